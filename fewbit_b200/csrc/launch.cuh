@@ -1,0 +1,143 @@
+// fewbit_b200 -- host-side launch helpers (grid sizing, aligned/ragged split).
+#pragma once
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "ops.cuh"
+
+#ifndef FEWBIT_U_F32
+#define FEWBIT_U_F32 2  // subtiles per warp tile, fp32: 4 LDG.128 in flight per lane
+#endif
+#ifndef FEWBIT_U_BF16
+#define FEWBIT_U_BF16 4  // bf16: 4 LDG.128 in flight per lane
+#endif
+
+namespace fewbit {
+
+// Arguments of the generic entry points, type-erased (see include/fewbit_b200.h).
+struct ForwardArgs {
+    int dtype;
+    const void *x;
+    void *y;
+    uint8_t *state;
+    int64_t n;
+    int bits;
+    const void *table;  // bounds
+    int ntable;
+    double p0, p1;
+    cudaStream_t stream;
+};
+struct BackwardArgs {
+    int dtype;
+    const uint8_t *state;
+    const void *gout;
+    void *gin;
+    int64_t n;
+    int bits;
+    const void *table;  // levels
+    int ntable;
+    double p0;
+    cudaStream_t stream;
+};
+
+void note_launch();  // api.cu: bumps fewbit_launch_count()
+int sm_count();      // api.cu: SM count of the current device (cached per device)
+
+template <typename T> constexpr int tile_subtiles() {
+    return sizeof(T) == 2 ? FEWBIT_U_BF16 : FEWBIT_U_F32;
+}
+
+// Resident CTAs per SM for `kernel` (occupancy API, cached per instantiation), overridable
+// with FEWBIT_B200_CTAS_PER_SM for tuning runs.
+template <auto kernel> int resident_ctas() {
+    static int cached = 0;
+    if (cached == 0) {
+        int blocks = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, kThreads, 0) !=
+                cudaSuccess ||
+            blocks < 1)
+            blocks = 1;
+        if (const char *env = std::getenv("FEWBIT_B200_CTAS_PER_SM")) {
+            int v = std::atoi(env);
+            if (v > 0) blocks = std::min(blocks, v);
+        }
+        cached = blocks;
+    }
+    return cached;
+}
+
+template <typename T> bool vector_aligned(const void *a, const void *b, const void *c) {
+    return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+             reinterpret_cast<uintptr_t>(c)) & 15u) == 0;
+}
+
+template <class Op, typename T>
+cudaError_t launch_forward(const T *x, T *y, uint8_t *state, int64_t n, const Op &op,
+                           cudaStream_t stream) {
+    constexpr int U = tile_subtiles<T>();
+    constexpr int64_t kTile = (int64_t)U * kSubtile;
+    if (n <= 0) return cudaSuccess;
+    const int64_t ntiles = vector_aligned<T>(x, y, state) ? n / kTile : 0;
+    if (ntiles > 0) {
+        constexpr auto kernel = forward_tiles_kernel<Op, T, U>;
+        const int64_t want = (ntiles + kWarps - 1) / kWarps;
+        const int64_t cap = (int64_t)sm_count() * resident_ctas<kernel>();
+        kernel<<<(unsigned)std::min(want, cap), kThreads, 0, stream>>>(x, y, state, ntiles, op);
+        note_launch();
+    }
+    const int64_t first = ntiles * kTile;
+    if (first < n) {
+        auto kernel = forward_ragged_kernel<Op, T>;
+        const int64_t octets = (n - first + 7) / 8;
+        const int64_t want = (octets + kThreads - 1) / kThreads;
+        const int64_t cap = (int64_t)sm_count() * 8;
+        kernel<<<(unsigned)std::min(want, cap), kThreads, 0, stream>>>(x, y, state, first, n, op);
+        note_launch();
+    }
+    return cudaGetLastError();
+}
+
+template <class Op, typename T>
+cudaError_t launch_backward(const uint8_t *state, const T *gout, T *gin, int64_t n, const Op &op,
+                            cudaStream_t stream) {
+    constexpr int U = tile_subtiles<T>();
+    constexpr int64_t kTile = (int64_t)U * kSubtile;
+    if (n <= 0) return cudaSuccess;
+    const int64_t ntiles = vector_aligned<T>(gout, gin, state) ? n / kTile : 0;
+    if (ntiles > 0) {
+        constexpr auto kernel = backward_tiles_kernel<Op, T, U>;
+        const int64_t want = (ntiles + kWarps - 1) / kWarps;
+        const int64_t cap = (int64_t)sm_count() * resident_ctas<kernel>();
+        kernel<<<(unsigned)std::min(want, cap), kThreads, 0, stream>>>(state, gout, gin, ntiles,
+                                                                       op);
+        note_launch();
+    }
+    const int64_t first = ntiles * kTile;
+    if (first < n) {
+        auto kernel = backward_ragged_kernel<Op, T>;
+        const int64_t octets = (n - first + 7) / 8;
+        const int64_t want = (octets + kThreads - 1) / kThreads;
+        const int64_t cap = (int64_t)sm_count() * 8;
+        kernel<<<(unsigned)std::min(want, cap), kThreads, 0, stream>>>(state, gout, gin, first, n,
+                                                                       op);
+        note_launch();
+    }
+    return cudaGetLastError();
+}
+
+// Expand `body(B)` for the run-time bit width.
+#define FEWBIT_DISPATCH_BITS(bits, BODY) \
+    switch (bits) {                      \
+        case 1: { constexpr int B = 1; BODY; } break; \
+        case 2: { constexpr int B = 2; BODY; } break; \
+        case 3: { constexpr int B = 3; BODY; } break; \
+        case 4: { constexpr int B = 4; BODY; } break; \
+        case 5: { constexpr int B = 5; BODY; } break; \
+        case 6: { constexpr int B = 6; BODY; } break; \
+        case 7: { constexpr int B = 7; BODY; } break; \
+        case 8: { constexpr int B = 8; BODY; } break; \
+        default: break;                  \
+    }
+
+}  // namespace fewbit

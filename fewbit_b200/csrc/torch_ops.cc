@@ -1,0 +1,295 @@
+// fewbit_b200 -- torch operator library `torch.ops.fewbit.*` (libfewbit.so).
+//
+// A thin layer: schema registration (verbatim from the reference, fewbit/fewbit.cc:5-39),
+// argument checks, allocation of the packed state, autograd bookkeeping (mark_dirty +
+// save_for_backward, as ContinousCudaFunction fewbit/cuda/activation.cc:337-382 and the
+// eight *CudaFunction classes :23-330), and one call into the C ABI (include/fewbit_b200.h)
+// per pass.  No arithmetic happens here and there is no CPU path: CUDA tensors only.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/library.h>
+#include <torch/torch.h>
+
+#include "fewbit_b200.h"
+
+namespace {
+
+using torch::Tensor;
+using torch::autograd::AutogradContext;
+using torch::autograd::variable_list;
+
+int dtype_code(const Tensor &t, const char *what) {
+    if (t.scalar_type() == torch::kFloat32) return FEWBIT_F32;
+    if (t.scalar_type() == torch::kBFloat16) return FEWBIT_BF16;
+    TORCH_CHECK(false, "fewbit: ", what, " must be float32 or bfloat16, got ", t.scalar_type());
+}
+
+void check_status(int status, const char *op) {
+    TORCH_CHECK(status == FEWBIT_OK, "fewbit::", op, " failed: ", fewbit_error_string(status));
+}
+
+void check_activation(const Tensor &self, const char *op) {
+    TORCH_CHECK(self.is_cuda(), "fewbit::", op,
+                ": expected a CUDA tensor (this library has no CPU path), got ", self.device());
+    TORCH_CHECK(self.is_contiguous(), "fewbit::", op, ": tensor must be contiguous");
+    dtype_code(self, "activation");
+}
+
+// Tables arrive already cast by the Python layer (functional/activations.py:212 of the
+// reference); direct callers (benchmark/bench-roberta.py:138-139) pass fp32 tables, so cast
+// and make them contiguous on the activation's device here.
+Tensor prepare_table(const Tensor &table, const Tensor &like, const char *what) {
+    TORCH_CHECK(table.dim() == 1, "fewbit: `", what, "` must be one-dimensional");
+    return table.to(like.device(), like.scalar_type()).contiguous();
+}
+
+Tensor new_state(const Tensor &like, int64_t n, int bits) {
+    auto opts = torch::TensorOptions().device(like.device()).dtype(torch::kUInt8);
+    return torch::empty({(int64_t)fewbit_state_bytes(n, bits)}, opts);
+}
+
+// ---------------------------------------------------------------- continuous family ----
+
+class StepwiseFunction : public torch::autograd::Function<StepwiseFunction> {
+public:
+    static Tensor forward(AutogradContext *ctx, const Tensor &self, const Tensor &bounds,
+                          const Tensor &levels, int64_t func, double p0, double p1) {
+        check_activation(self, "stepwise_forward");
+        TORCH_CHECK(levels.numel() >= 1 && levels.numel() <= 256,
+                    "fewbit: maximal number of steps is limited to 256, got ", levels.numel());
+        TORCH_CHECK(bounds.numel() + 1 == levels.numel(),
+                    "fewbit: size of `bounds` should be lesser than size of `levels` by one, got ",
+                    bounds.numel(), " and ", levels.numel());
+        c10::cuda::CUDAGuard guard(self.device());
+        auto stream = at::cuda::getCurrentCUDAStream();
+        const int bits = fewbit_bits_for_levels((int)levels.numel());
+        Tensor table = prepare_table(bounds, self, "bounds");
+        Tensor values = prepare_table(levels, self, "levels");
+        Tensor state = new_state(self, self.numel(), bits);
+        ctx->mark_dirty({self});
+        ctx->save_for_backward({state, values});
+        ctx->saved_data["bits"] = (int64_t)bits;
+        check_status(fewbit_stepwise_forward((int)func, dtype_code(self, "activation"),
+                                             self.data_ptr(), self.data_ptr(),
+                                             state.data_ptr<uint8_t>(), self.numel(), bits,
+                                             table.data_ptr(), (int)table.numel(), p0, p1,
+                                             stream.stream()),
+                     "stepwise_forward");
+        return self;
+    }
+
+    static variable_list backward(AutogradContext *ctx, variable_list grad_output) {
+        auto saved = ctx->get_saved_variables();
+        const Tensor &state = saved[0], &levels = saved[1];
+        const int bits = (int)ctx->saved_data["bits"].toInt();
+        Tensor gout = grad_output[0].contiguous();
+        TORCH_CHECK(gout.scalar_type() == levels.scalar_type(),
+                    "fewbit: gradient dtype ", gout.scalar_type(), " differs from activation dtype ",
+                    levels.scalar_type());
+        c10::cuda::CUDAGuard guard(gout.device());
+        auto stream = at::cuda::getCurrentCUDAStream();
+        Tensor gin = torch::empty_like(gout);
+        check_status(fewbit_stepwise_backward(dtype_code(gout, "gradient"),
+                                              state.data_ptr<uint8_t>(), gout.data_ptr(),
+                                              gin.data_ptr(), gout.numel(), bits, levels.data_ptr(),
+                                              (int)levels.numel(), stream.stream()),
+                     "stepwise_backward");
+        return {gin, Tensor(), Tensor(), Tensor(), Tensor(), Tensor()};
+    }
+};
+
+#define FEWBIT_CONTINUOUS0(name, id)                                                     \
+    Tensor name(Tensor &self, const Tensor &bounds, const Tensor &levels) {              \
+        return StepwiseFunction::apply(self, bounds, levels, (int64_t)(id), 0.0, 0.0);   \
+    }
+#define FEWBIT_CONTINUOUS1(name, id)                                                     \
+    Tensor name(Tensor &self, const Tensor &bounds, const Tensor &levels, double a) {    \
+        return StepwiseFunction::apply(self, bounds, levels, (int64_t)(id), a, 0.0);     \
+    }
+
+FEWBIT_CONTINUOUS1(celu, FEWBIT_CELU)
+FEWBIT_CONTINUOUS1(elu, FEWBIT_ELU)
+FEWBIT_CONTINUOUS0(gelu, FEWBIT_GELU)
+FEWBIT_CONTINUOUS0(hardswish, FEWBIT_HARDSWISH)
+FEWBIT_CONTINUOUS0(logsigmoid, FEWBIT_LOGSIGMOID)
+FEWBIT_CONTINUOUS0(mish, FEWBIT_MISH)
+FEWBIT_CONTINUOUS0(selu, FEWBIT_SELU)
+FEWBIT_CONTINUOUS0(sigmoid, FEWBIT_SIGMOID)
+FEWBIT_CONTINUOUS0(silu, FEWBIT_SILU)
+FEWBIT_CONTINUOUS0(softsign, FEWBIT_SOFTSIGN)
+FEWBIT_CONTINUOUS0(tanh_, FEWBIT_TANH)
+FEWBIT_CONTINUOUS0(tanhshrink, FEWBIT_TANHSHRINK)
+
+Tensor softplus(Tensor &self, const Tensor &bounds, const Tensor &levels, double beta,
+                double threshold) {
+    return StepwiseFunction::apply(self, bounds, levels, (int64_t)FEWBIT_SOFTPLUS, beta, threshold);
+}
+
+// ------------------------------------------------------------------- 1-bit family ----
+
+class PiecewiseFunction : public torch::autograd::Function<PiecewiseFunction> {
+public:
+    static Tensor forward(AutogradContext *ctx, const Tensor &self, int64_t func, double p0,
+                          double p1) {
+        check_activation(self, "piecewise_forward");
+        c10::cuda::CUDAGuard guard(self.device());
+        auto stream = at::cuda::getCurrentCUDAStream();
+        Tensor state = new_state(self, self.numel(), 1);
+        ctx->mark_dirty({self});
+        ctx->save_for_backward({state});
+        ctx->saved_data["func"] = func;
+        ctx->saved_data["p0"] = p0;  // plain double: no device sync in backward (the reference
+                                     // keeps the slope in a tensor and .item()s it)
+        check_status(fewbit_piecewise_forward((int)func, dtype_code(self, "activation"),
+                                              self.data_ptr(), self.data_ptr(),
+                                              state.data_ptr<uint8_t>(), self.numel(), p0, p1,
+                                              stream.stream()),
+                     "piecewise_forward");
+        return self;
+    }
+
+    static variable_list backward(AutogradContext *ctx, variable_list grad_output) {
+        auto saved = ctx->get_saved_variables();
+        Tensor gout = grad_output[0].contiguous();
+        c10::cuda::CUDAGuard guard(gout.device());
+        auto stream = at::cuda::getCurrentCUDAStream();
+        Tensor gin = torch::empty_like(gout);
+        check_status(fewbit_piecewise_backward((int)ctx->saved_data["func"].toInt(),
+                                               dtype_code(gout, "gradient"),
+                                               saved[0].data_ptr<uint8_t>(), gout.data_ptr(),
+                                               gin.data_ptr(), gout.numel(),
+                                               ctx->saved_data["p0"].toDouble(), stream.stream()),
+                     "piecewise_backward");
+        return {gin, Tensor(), Tensor(), Tensor()};
+    }
+};
+
+Tensor hardshrink(Tensor &self, double lambd) {
+    return PiecewiseFunction::apply(self, (int64_t)FEWBIT_HARDSHRINK, lambd, 0.0);
+}
+Tensor hardsigmoid(Tensor &self) {
+    return PiecewiseFunction::apply(self, (int64_t)FEWBIT_HARDSIGMOID, 0.0, 0.0);
+}
+Tensor hardtanh(Tensor &self, double min_val, double max_val) {
+    return PiecewiseFunction::apply(self, (int64_t)FEWBIT_HARDTANH, min_val, max_val);
+}
+Tensor leaky_relu(Tensor &self, double negative_slope) {
+    return PiecewiseFunction::apply(self, (int64_t)FEWBIT_LEAKY_RELU, negative_slope, 0.0);
+}
+Tensor relu(Tensor &self) { return PiecewiseFunction::apply(self, (int64_t)FEWBIT_RELU, 0.0, 0.0); }
+Tensor relu6(Tensor &self) {
+    return PiecewiseFunction::apply(self, (int64_t)FEWBIT_RELU6, 0.0, 0.0);
+}
+Tensor softshrink(Tensor &self, double lambd) {
+    return PiecewiseFunction::apply(self, (int64_t)FEWBIT_SOFTSHRINK, lambd, 0.0);
+}
+Tensor threshold(Tensor &self, double threshold, double value) {
+    return PiecewiseFunction::apply(self, (int64_t)FEWBIT_THRESHOLD, threshold, value);
+}
+
+// ------------------------------------------- quantize / quantize_backward (GELU) ----
+// Out-of-place pair of the reference (fewbit/cpu/gelu.cc:7-31, 33-45), here for CUDA tensors.
+
+std::tuple<Tensor, Tensor> quantize(const Tensor &inputs, const Tensor &bounds) {
+    check_activation(inputs, "quantize");
+    TORCH_CHECK(bounds.numel() >= 1 && bounds.numel() <= 255, "fewbit: 1..255 bounds expected");
+    c10::cuda::CUDAGuard guard(inputs.device());
+    auto stream = at::cuda::getCurrentCUDAStream();
+    const int bits = fewbit_bits_for_levels((int)bounds.numel() + 1);
+    Tensor table = prepare_table(bounds, inputs, "bounds");
+    Tensor outputs = torch::empty_like(inputs);
+    Tensor state = new_state(inputs, inputs.numel(), bits);
+    check_status(fewbit_stepwise_forward(FEWBIT_GELU, dtype_code(inputs, "inputs"),
+                                         inputs.data_ptr(), outputs.data_ptr(),
+                                         state.data_ptr<uint8_t>(), inputs.numel(), bits,
+                                         table.data_ptr(), (int)table.numel(), 0.0, 0.0,
+                                         stream.stream()),
+                 "quantize");
+    return {outputs, state};
+}
+
+Tensor quantize_backward(const Tensor &grads, const Tensor &buffer, const Tensor &levels) {
+    check_activation(grads, "quantize_backward");
+    TORCH_CHECK(buffer.is_cuda() && buffer.scalar_type() == torch::kUInt8 && buffer.is_contiguous(),
+                "fewbit::quantize_backward: `buffer` must be a contiguous CUDA uint8 tensor");
+    TORCH_CHECK(levels.numel() >= 1 && levels.numel() <= 256, "fewbit: 1..256 levels expected");
+    const int bits = fewbit_bits_for_levels((int)levels.numel());
+    TORCH_CHECK((size_t)buffer.numel() >= fewbit_state_bytes(grads.numel(), bits),
+                "fewbit::quantize_backward: `buffer` holds ", buffer.numel(), " bytes, ",
+                fewbit_state_bytes(grads.numel(), bits), " needed");
+    c10::cuda::CUDAGuard guard(grads.device());
+    auto stream = at::cuda::getCurrentCUDAStream();
+    Tensor values = prepare_table(levels, grads, "levels");
+    Tensor gin = torch::empty_like(grads);
+    check_status(fewbit_stepwise_backward(dtype_code(grads, "grads"), buffer.data_ptr<uint8_t>(),
+                                          grads.data_ptr(), gin.data_ptr(), grads.numel(), bits,
+                                          values.data_ptr(), (int)values.numel(), stream.stream()),
+                 "quantize_backward");
+    return gin;
+}
+
+}  // namespace
+
+// Schemas: verbatim from the reference (fewbit/fewbit.cc:6-37) -- they are the public ABI.
+TORCH_LIBRARY(fewbit, m) {
+    m.def("quantize(Tensor inputs, Tensor bounds) -> (Tensor, Tensor)");
+    m.def("quantize_backward(Tensor grads, Tensor buffer, Tensor levels) -> Tensor");
+
+    m.def("hardshrink (Tensor(a!) self, float lambd = 0.5) -> Tensor(a!)");
+    m.def("hardsigmoid(Tensor(a!) self) -> Tensor(a!)");
+    m.def("hardtanh   (Tensor(a!) self, float min_val = -1.0, float max_val = 1.0) -> Tensor(a!)");
+    m.def("leaky_relu (Tensor(a!) self, float negative_slope = 0.01) -> Tensor(a!)");
+    m.def("relu       (Tensor(a!) self) -> Tensor(a!)");
+    m.def("relu6      (Tensor(a!) self) -> Tensor(a!)");
+    m.def("softshrink (Tensor(a!) self, float lambd = 0.5) -> Tensor(a!)");
+    m.def("threshold  (Tensor(a!) self, float threshold, float value) -> Tensor(a!)");
+
+    m.def("celu      (Tensor(a!) self, Tensor bounds, Tensor levels, float alpha = 1.0) -> Tensor(a!)");
+    m.def("elu       (Tensor(a!) self, Tensor bounds, Tensor levels, float alpha = 1.0) -> Tensor(a!)");
+    m.def("gelu      (Tensor(a!) self, Tensor bounds, Tensor levels) -> Tensor(a!)");
+    m.def("hardswish (Tensor(a!) self, Tensor bounds, Tensor levels) -> Tensor(a!)");
+    m.def("logsigmoid(Tensor(a!) self, Tensor bounds, Tensor levels) -> Tensor(a!)");
+    m.def("mish      (Tensor(a!) self, Tensor bounds, Tensor levels) -> Tensor(a!)");
+    m.def("selu      (Tensor(a!) self, Tensor bounds, Tensor levels) -> Tensor(a!)");
+    m.def("sigmoid   (Tensor(a!) self, Tensor bounds, Tensor levels) -> Tensor(a!)");
+    m.def("silu      (Tensor(a!) self, Tensor bounds, Tensor levels) -> Tensor(a!)");
+    m.def("softplus  (Tensor(a!) self, Tensor bounds, Tensor levels, float beta = 1.0, float threshold = 20.0) -> Tensor(a!)");
+    m.def("softsign  (Tensor(a!) self, Tensor bounds, Tensor levels) -> Tensor(a!)");
+    m.def("tanh      (Tensor(a!) self, Tensor bounds, Tensor levels) -> Tensor(a!)");
+    m.def("tanhshrink(Tensor(a!) self, Tensor bounds, Tensor levels) -> Tensor(a!)");
+
+    // Declared by the reference without any kernel (fewbit/fewbit.cc:37); kept so that the
+    // schema set is identical.  Calling it raises NotImplementedError, as in the reference.
+    m.def("stepwise   (Tensor(a!) self, Tensor bounds, Tensor levels, bool? parity=None, int[2]? shift=None) -> Tensor(a!)");
+}
+
+// Same dispatch key as the reference (fewbit/cuda/activation.cc:445-470).
+TORCH_LIBRARY_IMPL(fewbit, AutogradCUDA, m) {
+    m.impl("hardshrink", hardshrink);
+    m.impl("hardsigmoid", hardsigmoid);
+    m.impl("hardtanh", hardtanh);
+    m.impl("leaky_relu", leaky_relu);
+    m.impl("relu", relu);
+    m.impl("relu6", relu6);
+    m.impl("softshrink", softshrink);
+    m.impl("threshold", threshold);
+
+    m.impl("celu", celu);
+    m.impl("elu", elu);
+    m.impl("gelu", gelu);
+    m.impl("hardswish", hardswish);
+    m.impl("logsigmoid", logsigmoid);
+    m.impl("mish", mish);
+    m.impl("selu", selu);
+    m.impl("sigmoid", sigmoid);
+    m.impl("silu", silu);
+    m.impl("softplus", softplus);
+    m.impl("softsign", softsign);
+    m.impl("tanh", tanh_);
+    m.impl("tanhshrink", tanhshrink);
+}
+
+TORCH_LIBRARY_IMPL(fewbit, CUDA, m) {
+    m.impl("quantize", quantize);
+    m.impl("quantize_backward", quantize_backward);
+}
