@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py -- FewBit hot path on B200: 1-bit mask pack + unpack on a 1 GiB bf16 tensor.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): per GPU one synthetic bf16 activation tensor of 2^29
+elements (1 GiB) and a gradient of the same size.  One *step* = for each of ReLU,
+LeakyReLU(0.01), Hardtanh(-1, 1): forward (y = f(x), 1-bit mask packed into 64 MiB) and
+backward (gin = factor(mask) * gout) -- six kernel launches through the C ABI
+(include/fewbit_b200.h).  Metric: algorithmic GB/s, bytes = n * (2 + 2 + 1/8) per pass
+(SURVEY 8d), summed over all GPUs (weak scaling: every rank owns its own shard, no collective
+on the data path).  Inputs are 8x larger than L2, so no flush is needed between iterations.
+
+One JSON line on stdout (rank 0); see the contract in the task description for the keys.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_ELEMS = 1 << 29                      # 1 GiB of bf16
+FUNCS = (('relu', 0.0, 0.0), ('leaky_relu', 0.01, 0.0), ('hardtanh', -1.0, 1.0))
+BYTES_PER_PASS = N_ELEMS * 2 + N_ELEMS * 2 + N_ELEMS // 8          # read + write + mask
+BYTES_PER_STEP = BYTES_PER_PASS * 2 * len(FUNCS)
+METRIC = 'mask_pack_unpack_throughput'
+UNIT = 'GB/s'
+CONFIG = {
+    'workload': '1-bit ReLU/LeakyReLU/Hardtanh mask pack+unpack, 1 GiB bf16 tensor per GPU '
+                '(BASELINE.json configs[1])',
+    'elements_per_gpu': N_ELEMS,
+    'functions': [f[0] for f in FUNCS],
+    'passes_per_step': 2 * len(FUNCS),
+    'algorithmic_bytes_per_step_per_gpu': BYTES_PER_STEP,
+    'l2_policy': 'inputs (2 GiB read per pass pair) are larger than the 126 MB L2; no flush needed',
+    'parallelism': 'batch-sharded replicas, no collective on the data path',
+}
+
+
+def measured_peak():
+    path = ROOT / 'MEASURED_PEAKS.json'
+    if path.exists():
+        try:
+            return float(json.loads(path.read_text())['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------- clocks ----
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the GPU is busy (B200_PROFILING.md recipe)."""
+    QUERY = ('clocks.sm,clocks.max.sm,utilization.gpu,power.draw,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
+                 '-lms', '50', '-i', str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, sm_max, reasons, total = [], [], set(), 0
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for stamp, line in self.rows:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 8:
+                continue
+            total += 1
+            try:
+                busy = float(parts[2]) >= 50.0
+            except ValueError:
+                busy = True
+            if not (t0 <= stamp <= t1 + 0.05) or not busy:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                sm_max.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[4:8]):
+                if flag.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None,
+                'sm_max_mhz': max(sm_max) if sm_max else None,
+                'reasons': sorted(reasons), 'samples_under_load': len(sm), 'samples': total}
+
+
+# ------------------------------------------------------------- CPU reference arm ----
+
+def cpu_reference_step(x, g, use_ref_codec):
+    """The reference's CPU implementation of one step on a sample: torch CPU ops for the value /
+    predicate / multiply (what fewbit/cpu/gelu.cc does with ATen) + the reference's own
+    single-threaded bit-stream codec fewbit::Deflate / Inflate (fewbit/cpu/codec.h) compiled
+    into oracle/_ref (the CPU *op* cannot run 1-bit tables, App. C-4).  Without
+    oracle/_ref the scalar C port (oracle/) stands in."""
+    import torch
+    import torch.nn.functional as F
+
+    import oracle
+    n = x.numel()
+    for name, p0, p1 in FUNCS:
+        if use_ref_codec:
+            if name == 'relu':
+                y, pred = F.relu(x), x > 0
+            elif name == 'leaky_relu':
+                y, pred = F.leaky_relu(x, p0), x < 0
+            else:
+                y, pred = F.hardtanh(x, p0, p1), (x > p0) & (x < p1)
+            state = oracle.ref_deflate(pred.to(torch.int32).numpy(), 1)
+            codes = torch.from_numpy(oracle.ref_inflate(state, n, 1))
+            if name == 'leaky_relu':
+                gin = torch.where(codes != 0, g * p0, g)
+            else:
+                gin = codes.to(g.dtype) * g
+            del y, gin
+        else:
+            bits = x.view(torch.int16).numpy().view('uint16')
+            gbits = g.view(torch.int16).numpy().view('uint16')
+            _, state = oracle.piecewise_forward(name, bits, p0, p1)
+            oracle.piecewise_backward(name, state, gbits, p0)
+
+
+def run_reference_arm(args, rank, world):
+    """`--impl reference`: the reference CPU path on the host cores, rank 0 only."""
+    if rank != 0:
+        return
+    import torch
+
+    import oracle
+    use_ref = oracle.ref_codec() is not None
+    torch.manual_seed(0)
+    probe = 1 << 20
+    x = (torch.randn(probe) * 2).to(torch.bfloat16)
+    g = torch.randn(probe).to(torch.bfloat16)
+    cpu_reference_step(x, g, use_ref)
+    t = time.perf_counter()
+    cpu_reference_step(x, g, use_ref)
+    per_elem = (time.perf_counter() - t) / probe
+    budget = 90.0 / max(1, args.steps + args.warmup)          # whole run within ~1.5 minutes
+    sample = int(min(1 << 26, max(1 << 20, budget / per_elem)))
+    sample -= sample % 2048
+    x = (torch.randn(sample) * 2).to(torch.bfloat16)
+    g = torch.randn(sample).to(torch.bfloat16)
+    for _ in range(args.warmup):
+        cpu_reference_step(x, g, use_ref)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(x, g, use_ref)
+    elapsed = time.perf_counter() - t0
+    nbytes = (sample * 4 + sample // 8) * 2 * len(FUNCS)
+    value = nbytes * args.steps / elapsed / 1e9
+    cores = torch.get_num_threads()
+    kind = 'reference' if use_ref else 'port'
+    sample_txt = (f'{sample} bf16 elements per step ({sample * 2 / 2**20:.0f} MiB; the full workload '
+                  f'is {N_ELEMS}), same three functions, fwd+bwd')
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': elapsed / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+        'data': 'synthetic', 'config': CONFIG,
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind,
+                         'sample': sample_txt},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }))
+
+
+def cpu_baseline_leg():
+    """Bounded (~10-30 s) timing of the reference CPU path inside our arm (rank 0, N=1)."""
+    import torch
+
+    import oracle
+    use_ref = oracle.ref_codec() is not None
+    sample = 1 << 25
+    torch.manual_seed(0)
+    x = (torch.randn(sample) * 2).to(torch.bfloat16)
+    g = torch.randn(sample).to(torch.bfloat16)
+    cpu_reference_step(x, g, use_ref)
+    reps, t0 = 0, time.perf_counter()
+    while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 50):
+        cpu_reference_step(x, g, use_ref)
+        reps += 1
+    elapsed = time.perf_counter() - t0
+    nbytes = (sample * 4 + sample // 8) * 2 * len(FUNCS)
+    return {'value': nbytes * reps / elapsed / 1e9, 'unit': UNIT, 'cores': torch.get_num_threads(),
+            'kind': 'reference' if use_ref else 'port',
+            'sample': f'{reps} steps over {sample} bf16 elements ({sample * 2 >> 20} MiB of the 1 GiB '
+                      f'workload), {elapsed:.1f} s; torch CPU ops + fewbit::Deflate/Inflate '
+                      f'(fewbit/cpu/codec.h, single-threaded by construction)'}
+
+
+# ------------------------------------------------------------------------ our arm ----
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from fewbit_b200 import native
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the product path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    torch.manual_seed(1234 + rank)
+    x = torch.empty(N_ELEMS, dtype=torch.bfloat16, device=dev).normal_(0, 2)
+    g = torch.empty(N_ELEMS, dtype=torch.bfloat16, device=dev).normal_()
+    y, gin = torch.empty_like(x), torch.empty_like(g)
+    state = native.new_state(x, 1)
+    stream = torch.cuda.current_stream()
+
+    def step(marks=None):
+        for name, p0, p1 in FUNCS:
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True); e.record(stream); marks.append(e)
+            native.piecewise_forward(name, x, y, state, p0, p1, stream)
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True); e.record(stream); marks.append(e)
+            native.piecewise_backward(name, state, g, gin, p0, stream)
+        if marks is not None:
+            e = torch.cuda.Event(enable_timing=True); e.record(stream); marks.append(e)
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_busy0 = time.perf_counter()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    fence()
+    launches0 = native.launch_count()
+    marks_all = []
+    begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    begin.record(stream)
+    for _ in range(args.steps):
+        marks = []
+        step(marks)
+        marks_all.append(marks)
+    end.record(stream)
+    fence()
+    launches = native.launch_count() - launches0
+    elapsed_ms = begin.elapsed_time(end)
+    t_busy1 = time.perf_counter()
+
+    # per-kernel device times from the events recorded inside the timed region
+    per_kernel = {}
+    for marks in marks_all:
+        for i, (name, _, _) in enumerate(FUNCS):
+            per_kernel.setdefault(f'{name}_forward', []).append(marks[2 * i].elapsed_time(marks[2 * i + 1]))
+            per_kernel.setdefault(f'{name}_backward', []).append(marks[2 * i + 1].elapsed_time(marks[2 * i + 2]))
+    kernel_ms = {k: sum(v) / len(v) for k, v in per_kernel.items()}
+
+    # ---- end to end through the host-buffer C ABI (pinned host memory, copies inside) ----
+    e2e_steps = max(1, min(args.steps, 3))
+    xh = torch.empty(N_ELEMS, dtype=torch.bfloat16).pin_memory()
+    gh = torch.empty(N_ELEMS, dtype=torch.bfloat16).pin_memory()
+    xh.copy_(x); gh.copy_(g)
+    yh, ginh = torch.empty_like(xh).pin_memory(), torch.empty_like(gh).pin_memory()
+
+    def e2e_step():
+        for name, p0, p1 in FUNCS:
+            native.piecewise_forward_host(name, xh, yh, state, p0, p1)
+            native.piecewise_backward_host(name, state, gh, ginh, p0)
+
+    e2e_step()
+    fence()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_launches = None
+    fence()
+    t_busy2 = time.perf_counter()
+    clocks = sampler.stop(t_busy0, t_busy2) if sampler else None
+
+    # ---- max over ranks ----
+    times = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    elapsed_ms, e2e_ms = times.tolist()
+
+    extra = {}
+    if rank == 0 and world == 1:
+        extra = side_measurements(dev)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        value = world * BYTES_PER_STEP * args.steps / (elapsed_ms / 1e3) / 1e9
+        e2e_value = world * BYTES_PER_STEP * e2e_steps / (e2e_ms / 1e3) / 1e9
+        dominant = 'relu_forward'
+        achieved = BYTES_PER_PASS / (kernel_ms[dominant] / 1e3) / 1e9
+        traffic = None
+        tpath = ROOT / 'profiles' / 'ncu_traffic.json'
+        if tpath.exists():
+            try:
+                traffic = json.loads(tpath.read_text()).get(dominant)
+            except Exception:  # noqa: BLE001
+                traffic = None
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': elapsed_ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+            'data': 'synthetic', 'config': CONFIG,
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                         'frac': achieved / peak, 'traffic': traffic, 'kernel': dominant,
+                         'peak_source': peak_src, 'algorithmic_bytes_per_launch': BYTES_PER_PASS,
+                         'avg_launch_ms': kernel_ms[dominant]},
+            'kernels_GBps': {k: BYTES_PER_PASS / (v / 1e3) / 1e9 for k, v in kernel_ms.items()},
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'steps': e2e_steps,
+                    'h2d_bytes_per_step': 2 * len(FUNCS) * N_ELEMS * 2,
+                    'd2h_bytes_per_step': 2 * len(FUNCS) * N_ELEMS * 2,
+                    'api': 'fewbit_piecewise_{forward,backward}_host (pinned host buffers, chunked '
+                           'H2D -> kernel -> D2H on 3 streams)'},
+            'gpu_launches': launches,
+            'clocks': clocks,
+        }
+        if world == 1:
+            line['cpu_baseline'] = cpu_baseline_leg()
+        if extra:
+            line['extra'] = extra
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def side_measurements(dev):
+    """Not part of the headline: 3-bit GELU on 128 x 128 x 3072 (configs[0]/[2]), fp32 and bf16,
+    forward and backward GB/s, median of 20 after 5 warm-ups."""
+    import torch
+
+    from fewbit_b200 import native
+    from fewbit_b200.functional import store
+    out = {}
+    n = 128 * 128 * 3072
+    for tag, dtype, es in (('f32', torch.float32, 4), ('bf16', torch.bfloat16, 2)):
+        borders, levels = store.get('gelu', 3, dev, dtype)
+        bounds = borders[1:-1].contiguous()
+        x = (torch.randn(n, device=dev) * 2).to(dtype)
+        g = torch.randn(n, device=dev).to(dtype)
+        y, gin = torch.empty_like(x), torch.empty_like(g)
+        state = native.new_state(x, 3)
+        nbytes = n * (2 * es) + n * 3 // 8
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        for label, fn in (('fwd', lambda: native.stepwise_forward('gelu', x, y, state, 3, bounds)),
+                          ('bwd', lambda: native.stepwise_backward(state, g, gin, 3, levels))):
+            ts = []
+            for it in range(25):
+                flush.zero_()                                  # 256 MiB > L2: cold inputs
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                torch.cuda.synchronize()
+                if it >= 5:
+                    ts.append(a.elapsed_time(b))
+            out[f'gelu3_{tag}_{label}_GBps'] = nbytes / (statistics.median(ts) / 1e3) / 1e9
+        del x, g, y, gin, state, flush
+    out['note'] = '128x128x3072 elements, median of 20 launches, L2 flushed between launches'
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if args.impl == 'reference':
+        run_reference_arm(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,125 @@
+"""Linear layer whose weight gradient is estimated from a random sketch of the token axis
+(reference ``fewbit/functional/linear.py:69-221``, ``LinearGRPFunc``).
+
+Forward is an exact ``F.linear``; instead of the input ``X`` (N x in) only the sketch
+``X_proj = S X / P`` (P x in) is saved, with ``S`` (P x N) Gaussian or Rademacher.  Backward
+regenerates the same ``S`` from the saved generator state and returns
+
+    grad_input = G W            (exact)
+    grad_weight = (S G)^T X_proj   (unbiased estimate of G^T X)
+    grad_bias  = sum_n G        (exact)
+
+Deliberate fixes: without a user generator the CUDA path draws from the
+device's *default* generator (the reference builds a fresh default-seeded generator per call,
+i.e. the same ``S`` in every layer and step), and ``S`` is created in the input dtype.
+"""
+from __future__ import annotations
+
+from typing import Literal, Optional
+
+import torch as T
+import torch.nn.functional as F
+
+__all__ = ('linear_grp', 'linear_randomized', 'calc_proj_dim')
+
+MatMulType = Literal['gaussian', 'rademacher', 'dct', 'dft']
+
+
+def clamp(val: int, minval: Optional[int] = None, maxval: Optional[int] = None) -> int:
+    # Falsy bounds are ignored, exactly as reference functional/linear.py:17-24.
+    if minval:
+        val = max(minval, val)
+    if maxval:
+        val = min(maxval, val)
+    return val
+
+
+def calc_proj_dim(ndim: int, proj_dim_ratio: Optional[float], proj_dim: Optional[int],
+                  proj_dim_max: Optional[int], proj_dim_min: Optional[int]) -> int:
+    """P = proj_dim or int(ratio * N) or N, then clamped (reference :72-81)."""
+    if proj_dim:
+        result = proj_dim
+    elif proj_dim_ratio:
+        result = int(proj_dim_ratio * ndim)
+    else:
+        result = ndim
+    return clamp(result, proj_dim_min, proj_dim_max)
+
+
+def _default_generator(device: T.device) -> T.Generator:
+    if device.type == 'cuda':
+        index = device.index if device.index is not None else T.cuda.current_device()
+        return T.cuda.default_generators[index]
+    return T.default_generator
+
+
+def _sketch_matrix(kind: str, rows: int, cols: int, generator: T.Generator, device, dtype):
+    """The random matrix S (rows x cols): N(0,1) entries or +-1/2 (reference :133-146)."""
+    if kind == 'gaussian':
+        return T.randn((rows, cols), generator=generator, device=device, dtype=dtype)
+    if kind == 'rademacher':
+        return T.randint(high=2, size=(rows, cols), generator=generator, device=device,
+                         dtype=dtype) - 0.5
+    if kind in ('dct', 'dft'):
+        raise NotImplementedError(f"matmul='{kind}' is outside the B200 hot path (SURVEY 2.1 #8); "
+                                  "use 'gaussian' or 'rademacher'.")
+    raise ValueError(f'Unexpected matmul type: {kind}.')
+
+
+class LinearGRPFunc(T.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, input: T.Tensor, weight: T.Tensor, bias: Optional[T.Tensor],
+                proj_dim_ratio: Optional[float], proj_dim: Optional[int],
+                proj_dim_max: Optional[int], proj_dim_min: Optional[int], matmul: MatMulType,
+                generator: Optional[T.Generator]) -> T.Tensor:
+        if proj_dim_ratio is None and proj_dim is None:
+            raise ValueError('Either proj_dim or proj_dim_ratio should be specified.')
+        if proj_dim_min and proj_dim_min <= 0:
+            raise ValueError('Param proj_dim_min should be strictly positive.')
+        if proj_dim_min and proj_dim_max and proj_dim_max < proj_dim_min:
+            raise ValueError('Param proj_dim_min should be not greater than param proj_dim_max.')
+
+        generator = generator or _default_generator(input.device)
+        generator_state = generator.get_state()
+
+        input_view = input.reshape(-1, input.shape[-1])
+        proj_features = calc_proj_dim(input_view.shape[0], proj_dim_ratio, proj_dim, proj_dim_max,
+                                      proj_dim_min)
+        proj = _sketch_matrix(matmul, proj_features, input_view.shape[0], generator, input.device,
+                              input.dtype)
+        # E[S^T S] = P I (gaussian) or P/4 I (rademacher): scale so that E[grad_weight] = G^T X,
+        # with the very arithmetic of the reference (:137, :146).
+        if matmul == 'gaussian':
+            input_proj = (proj @ input_view) / proj_features
+        else:
+            input_proj = (proj @ input_view) * (4 / proj_features)
+        del proj
+
+        ctx.save_for_backward(input_proj, weight, bias)
+        ctx.proj_features = proj_features
+        ctx.matmul = matmul
+        ctx.generator_state = generator_state
+        ctx.generator_device = generator.device
+        return F.linear(input, weight, bias)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input_proj, weight, bias = ctx.saved_tensors
+        grad_input = grad_weight = grad_bias = None
+        if ctx.needs_input_grad[0]:
+            grad_input = grad_output @ weight
+        if ctx.needs_input_grad[1]:
+            generator = T.Generator(ctx.generator_device)
+            generator.set_state(ctx.generator_state)
+            grad_view = grad_output.reshape(-1, grad_output.shape[-1])
+            proj = _sketch_matrix(ctx.matmul, ctx.proj_features, grad_view.shape[0], generator,
+                                  grad_output.device, grad_output.dtype)
+            grad_weight = (proj @ grad_view).T @ input_proj
+        if bias is not None and ctx.needs_input_grad[2]:
+            grad_bias = grad_output.reshape(-1, grad_output.shape[-1]).sum(dim=0)
+        return (grad_input, grad_weight, grad_bias) + (None, ) * 6
+
+
+linear_grp = LinearGRPFunc.apply
+linear_randomized = linear_grp

@@ -1,0 +1,64 @@
+"""``RandomizedLinear`` / ``LinearGRP`` (reference ``fewbit/modules/linear.py:39-146``)."""
+from __future__ import annotations
+
+from typing import Literal, Optional
+
+import torch as T
+
+from ..functional.linear import linear_grp
+
+__all__ = ('LinearGRP', 'RandomizedLinear')
+
+MatMulType = Literal['gaussian', 'rademacher', 'dct', 'dft']
+
+
+class LinearGRP(T.nn.Linear):
+    r"""``torch.nn.Linear`` that keeps a random projection of its input for backward.
+
+    Approximates the weight gradient with Gaussian (or Rademacher) random projections along
+    the batch/token axis, as in `Memory-Efficient Backpropagation through Large Linear Layers
+    <https://arxiv.org/abs/2201.13195>`_; the forward pass :math:`y = xA^T + b` is exact.
+
+    Args:
+        in_features, out_features, bias, device, dtype: as :class:`torch.nn.Linear`.
+        proj_dim_ratio: projection size as a fraction of the number of input rows.
+        proj_dim: exact projection size (takes precedence over the ratio).
+        proj_dim_min, proj_dim_max: clamp of the projection size.
+        matmul: ``'gaussian'`` (default) or ``'rademacher'``.
+        generator: random generator; default is the device's global generator.
+
+    Either ``proj_dim_ratio`` or ``proj_dim`` must be given.
+
+    Example::
+
+        >>> m = fewbit.RandomizedLinear(20, 30, proj_dim_ratio=0.5)
+        >>> m(torch.randn(128, 20)).size()
+        torch.Size([128, 30])
+    """
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, device=None,
+                 dtype=None, proj_dim_ratio: Optional[float] = None,
+                 proj_dim: Optional[int] = None, proj_dim_min: Optional[int] = None,
+                 proj_dim_max: Optional[int] = None, matmul: MatMulType = 'gaussian',
+                 generator: Optional[T.Generator] = None) -> None:
+        super().__init__(in_features, out_features, bias, device, dtype)
+        self.generator = generator
+        self.matmul = matmul
+        self.proj_dim_ratio = proj_dim_ratio
+        self.proj_dim = proj_dim
+        self.proj_dim_max = proj_dim_max
+        self.proj_dim_min = proj_dim_min
+
+    def forward(self, input: T.Tensor) -> T.Tensor:
+        return linear_grp(input, self.weight, self.bias, self.proj_dim_ratio, self.proj_dim,
+                          self.proj_dim_max, self.proj_dim_min, self.matmul, self.generator)
+
+    def extra_repr(self) -> str:
+        return ', '.join([
+            super().extra_repr(), f'matmul={self.matmul}', f'proj_dim={self.proj_dim}',
+            f'proj_dim_ratio={self.proj_dim_ratio}', f'proj_dim_max={self.proj_dim_max}',
+            f'proj_dim_min={self.proj_dim_min}'
+        ])
+
+
+RandomizedLinear = LinearGRP

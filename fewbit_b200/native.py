@@ -1,0 +1,167 @@
+"""ctypes binding of the C ABI (``include/fewbit_b200.h``, ``libfewbit_b200.so``).
+
+This is the same boundary a non-Python host (cgo, JNI, ...) would bind; the parity tests and
+``bench.py`` call the kernels through it with raw device pointers taken from torch tensors.
+Every wrapper raises ``RuntimeError`` on a non-zero status -- nothing falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+LIBRARY = Path(__file__).with_name('libfewbit_b200.so')
+
+F32, BF16 = 0, 1
+CONTINUOUS = ('celu', 'elu', 'gelu', 'hardswish', 'logsigmoid', 'mish', 'selu', 'sigmoid', 'silu',
+              'softplus', 'softsign', 'tanh', 'tanhshrink')
+PIECEWISE = ('hardshrink', 'hardsigmoid', 'hardtanh', 'leaky_relu', 'relu', 'relu6', 'softshrink',
+             'threshold')
+
+# name -> (restype, argtypes): must list every symbol include/fewbit_b200.h declares
+# (tests/test_abi.py checks both directions).
+_vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
+PROTOTYPES = {
+    'fewbit_abi_version': (_i, []),
+    'fewbit_error_string': (C.c_char_p, [_i]),
+    'fewbit_state_bytes': (C.c_size_t, [_i64, _i]),
+    'fewbit_bits_for_levels': (_i, [_i]),
+    'fewbit_stepwise_forward': (_i, [_i, _i, _vp, _vp, _vp, _i64, _i, _vp, _i, _d, _d, _vp]),
+    'fewbit_stepwise_backward': (_i, [_i, _vp, _vp, _vp, _i64, _i, _vp, _i, _vp]),
+    'fewbit_piecewise_forward': (_i, [_i, _i, _vp, _vp, _vp, _i64, _d, _d, _vp]),
+    'fewbit_piecewise_backward': (_i, [_i, _i, _vp, _vp, _vp, _i64, _d, _vp]),
+    'fewbit_deflate': (_i, [_vp, _vp, _i64, _i, _vp]),
+    'fewbit_inflate': (_i, [_vp, _vp, _i64, _i, _vp]),
+    'fewbit_stepwise_forward_host': (_i, [_i, _i, _vp, _vp, _vp, _i64, _i, _vp, _i, _d, _d, _i64]),
+    'fewbit_stepwise_backward_host': (_i, [_i, _vp, _vp, _vp, _i64, _i, _vp, _i, _i64]),
+    'fewbit_piecewise_forward_host': (_i, [_i, _i, _vp, _vp, _vp, _i64, _d, _d, _i64]),
+    'fewbit_piecewise_backward_host': (_i, [_i, _i, _vp, _vp, _vp, _i64, _d, _i64]),
+    'fewbit_launch_count': (_i64, []),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIBRARY.exists():
+            raise RuntimeError(f'{LIBRARY} is missing: build it with `python -c "import '
+                               f'__graft_entry__ as g; g.build()"` or `make -C fewbit_b200/csrc`.')
+        handle = C.CDLL(str(LIBRARY))
+        for name, (restype, argtypes) in PROTOTYPES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = restype, argtypes
+        _lib = handle
+    return _lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        raise RuntimeError(f'{what} failed ({status}): {lib().fewbit_error_string(status).decode()}')
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f'fewbit_b200: unsupported dtype {t.dtype}')
+
+
+def _func(table, func) -> int:
+    return table.index(func) if isinstance(func, str) else int(func)
+
+
+def _stream(stream=None) -> int:
+    if stream is None:
+        stream = torch.cuda.current_stream()
+    return stream.cuda_stream
+
+
+def state_bytes(n: int, bits: int) -> int:
+    return int(lib().fewbit_state_bytes(n, bits))
+
+
+def bits_for_levels(nlevels: int) -> int:
+    return int(lib().fewbit_bits_for_levels(nlevels))
+
+
+def launch_count() -> int:
+    return int(lib().fewbit_launch_count())
+
+
+def new_state(x: torch.Tensor, bits: int) -> torch.Tensor:
+    return torch.empty(state_bytes(x.numel(), bits), dtype=torch.uint8, device=x.device)
+
+
+def stepwise_forward(func, x, y, state, bits, bounds, p0=1.0, p1=20.0, stream=None):
+    """y = f(x) (y may be x), state = pack(bucketize(x, bounds), bits).  Device tensors."""
+    check(lib().fewbit_stepwise_forward(_func(CONTINUOUS, func), dtype_code(x), x.data_ptr(),
+                                        y.data_ptr(), state.data_ptr(), x.numel(), bits,
+                                        bounds.data_ptr(), bounds.numel(), p0, p1, _stream(stream)),
+          'fewbit_stepwise_forward')
+
+
+def stepwise_backward(state, gout, gin, bits, levels, stream=None):
+    check(lib().fewbit_stepwise_backward(dtype_code(gout), state.data_ptr(), gout.data_ptr(),
+                                         gin.data_ptr(), gout.numel(), bits, levels.data_ptr(),
+                                         levels.numel(), _stream(stream)),
+          'fewbit_stepwise_backward')
+
+
+def piecewise_forward(func, x, y, state, p0=0.0, p1=0.0, stream=None):
+    check(lib().fewbit_piecewise_forward(_func(PIECEWISE, func), dtype_code(x), x.data_ptr(),
+                                         y.data_ptr(), state.data_ptr(), x.numel(), p0, p1,
+                                         _stream(stream)),
+          'fewbit_piecewise_forward')
+
+
+def piecewise_backward(func, state, gout, gin, p0=0.0, stream=None):
+    check(lib().fewbit_piecewise_backward(_func(PIECEWISE, func), dtype_code(gout),
+                                          state.data_ptr(), gout.data_ptr(), gin.data_ptr(),
+                                          gout.numel(), p0, _stream(stream)),
+          'fewbit_piecewise_backward')
+
+
+def deflate(codes, state, bits, stream=None):
+    check(lib().fewbit_deflate(codes.data_ptr(), state.data_ptr(), codes.numel(), bits,
+                               _stream(stream)), 'fewbit_deflate')
+
+
+def inflate(state, codes, bits, stream=None):
+    check(lib().fewbit_inflate(state.data_ptr(), codes.data_ptr(), codes.numel(), bits,
+                               _stream(stream)), 'fewbit_inflate')
+
+
+# Host-buffer variants: x/y/gout/gin are (pinned) HOST tensors, state and tables stay on device.
+
+def stepwise_forward_host(func, x_host, y_host, state, bits, bounds, p0=1.0, p1=20.0, chunk=0):
+    check(lib().fewbit_stepwise_forward_host(_func(CONTINUOUS, func), dtype_code(x_host),
+                                             x_host.data_ptr(), y_host.data_ptr(),
+                                             state.data_ptr(), x_host.numel(), bits,
+                                             bounds.data_ptr(), bounds.numel(), p0, p1, chunk),
+          'fewbit_stepwise_forward_host')
+
+
+def stepwise_backward_host(state, gout_host, gin_host, bits, levels, chunk=0):
+    check(lib().fewbit_stepwise_backward_host(dtype_code(gout_host), state.data_ptr(),
+                                              gout_host.data_ptr(), gin_host.data_ptr(),
+                                              gout_host.numel(), bits, levels.data_ptr(),
+                                              levels.numel(), chunk),
+          'fewbit_stepwise_backward_host')
+
+
+def piecewise_forward_host(func, x_host, y_host, state, p0=0.0, p1=0.0, chunk=0):
+    check(lib().fewbit_piecewise_forward_host(_func(PIECEWISE, func), dtype_code(x_host),
+                                              x_host.data_ptr(), y_host.data_ptr(),
+                                              state.data_ptr(), x_host.numel(), p0, p1, chunk),
+          'fewbit_piecewise_forward_host')
+
+
+def piecewise_backward_host(func, state, gout_host, gin_host, p0=0.0, chunk=0):
+    check(lib().fewbit_piecewise_backward_host(_func(PIECEWISE, func), dtype_code(gout_host),
+                                               state.data_ptr(), gout_host.data_ptr(),
+                                               gin_host.data_ptr(), gout_host.numel(), p0, chunk),
+          'fewbit_piecewise_backward_host')

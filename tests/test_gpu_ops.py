@@ -1,0 +1,238 @@
+"""torch.ops.fewbit / fewbit.functional / modules on CUDA tensors: the reference's own tests
+restated (fewbit/functional/activations_test.py), in-place + autograd semantics, errors."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import fewbit_b200 as fewbit
+import oracle
+from fewbit_b200 import functional as FF
+from fewbit_b200.functional import CONTINOUS, store
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _loaded_native():
+    assert fewbit.native_loaded(), fewbit.NATIVE_ERROR
+
+
+# ---- reference tests, restated ----------------------------------------------------------
+
+PIECEWISE = [('hardshrink', {}), ('hardshrink', {'lambd': 1.0}), ('hardsigmoid', {}), ('hardtanh', {}),
+             ('hardtanh', {'min_val': -2.0, 'max_val': 2.0}), ('leaky_relu', {}),
+             ('leaky_relu', {'negative_slope': 0.5}), ('relu', {}), ('relu6', {}), ('softshrink', {}),
+             ('softshrink', {'lambd': 1.0})]
+
+
+@pytest.mark.parametrize('name,kwargs', PIECEWISE)
+def test_reference_stepwise_testcase(name, kwargs):
+    # activations_test.py:17-32: value and gradient vs torch on linspace(-5, 5, 101), places=6
+    _loaded_native()
+    xs = torch.linspace(-5, 5, 101).to(DEV)
+    gs = torch.ones_like(xs)
+    ps = xs.clone().requires_grad_()
+    ys = getattr(F, name)(ps, **kwargs)
+    ys.backward(gs)
+    qs = xs.clone().requires_grad_()
+    zs = getattr(FF, name)(qs.clone(), **kwargs)
+    zs.backward(gs)
+    assert torch.linalg.norm(zs - ys).item() < 5e-7
+    assert torch.linalg.norm(ps.grad - qs.grad).item() < 5e-7
+
+
+def test_reference_threshold_testcase():
+    xs = torch.linspace(-5, 5, 101).to(DEV)
+    ps = xs.clone().requires_grad_()
+    F.threshold(ps, 1.0, 3.0).backward(torch.ones_like(xs))
+    qs = xs.clone().requires_grad_()
+    zs = FF.threshold(qs.clone(), 1.0, 3.0)
+    zs.backward(torch.ones_like(xs))
+    assert torch.linalg.norm(zs - F.threshold(xs, 1.0, 3.0)).item() < 5e-7
+    assert torch.linalg.norm(ps.grad - qs.grad).item() < 5e-7
+
+
+@pytest.mark.parametrize('name', CONTINOUS)
+def test_reference_continuous_testcase(name):
+    # activations_test.py:79-104: forward L2 < 1e-6 on 101 points; here also the CUDA backward,
+    # which the reference never compares to anything.
+    xs = torch.linspace(-5, 5, 101).to(DEV)
+    ref = (getattr(F, name, None) or getattr(torch, name))(xs)
+    qs = xs.clone().requires_grad_()
+    zs = getattr(FF, name)(qs.clone(), bits=3)
+    assert torch.linalg.norm(zs - ref).item() < 1e-6
+    zs.backward(torch.ones_like(zs))
+    borders, levels = store.get(name, 3, DEV, torch.float32)
+    want = levels[torch.searchsorted(borders[1:-1].contiguous(), xs)]
+    assert torch.equal(qs.grad, want)
+
+
+@pytest.mark.parametrize('name', CONTINOUS)
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_forward_matches_torch_cuda_kernels(name, dtype):
+    """Secondary criterion of SURVEY App. A on N(0, 2^2) inputs: fp32 within max(4 ulp, 2.5e-7)
+    of the ATen CUDA result; bf16 within one bf16 ulp."""
+    torch.manual_seed(11)
+    x = (torch.randn(1 << 20, device=DEV) * 2).to(dtype)
+    args = {'celu': (1.5, ), 'elu': (0.7, ), 'softplus': (2.0, 10.0)}.get(name, ())
+    ref = (getattr(F, name, None) or getattr(torch, name))(x, *args)
+    y = getattr(FF, name)(x.clone(), *args, bits=2)
+    if dtype == torch.float32:
+        tol = 4 * (torch.nextafter(ref.abs(), ref.abs() + 1) - ref.abs()) + 2.5e-7
+    else:
+        tol = ref.float().abs() * 2.0 ** -7 + 1e-6
+    err = (y.float() - ref.float()).abs()
+    assert torch.all(err <= tol), f'{name}: max err {err.max().item():.3e}'
+
+
+# ---- operator semantics -------------------------------------------------------------------
+
+def test_in_place_and_only_codes_are_saved():
+    n = 1 << 22
+    x = torch.randn(n, device=DEV)
+    leaf = x.clone().requires_grad_()
+    h = leaf * 1.0
+    ptr = h.data_ptr()
+    torch.cuda.synchronize()
+    before = torch.cuda.memory_allocated()
+    y = FF.gelu(h, bits=3)
+    torch.cuda.synchronize()
+    grown = torch.cuda.memory_allocated() - before
+    assert y.data_ptr() == ptr                                  # Tensor(a!) -> Tensor(a!)
+    assert torch.equal(h, y)                                    # the input now holds f(x)
+    assert n * 3 // 8 <= grown <= n * 3 // 8 + (2 << 20)        # nothing but the packed codes
+    assert torch.allclose(y, F.gelu(x), atol=1e-6)
+    y.sum().backward()
+    assert leaf.grad is not None and leaf.grad.shape == x.shape
+
+
+def test_direct_operator_call_like_bench_roberta():
+    # benchmark/bench-roberta.py:128-139: T.ops.fewbit.gelu(xs, bounds7, levels8), fp32 tables
+    from test_oracle import BOUNDS, LEVELS
+    bounds, levels = torch.from_numpy(BOUNDS).to(DEV), torch.from_numpy(LEVELS).to(DEV)
+    for dtype in (torch.float32, torch.bfloat16):
+        x = (torch.randn(4, 128, 3072, device=DEV) * 2).to(dtype)
+        h = x.clone().requires_grad_()
+        y = torch.ops.fewbit.gelu(h + 0, bounds, levels)        # tables are cast to x.dtype inside
+        g = torch.randn_like(y)
+        y.backward(g)
+        codes = torch.searchsorted(bounds.to(dtype).float(), x.float().flatten()).view_as(x)
+        want = (levels.to(dtype).float()[codes] * g.float()).to(dtype)
+        assert torch.equal(h.grad, want)
+
+
+def test_quantize_pair_matches_reference_cpu_ops(golden_ops):
+    """torch.ops.fewbit.quantize / quantize_backward on CUDA == the reference on CPU."""
+    for case in golden_ops[::5]:
+        if case['bf16']:
+            conv = lambda a: torch.from_numpy(a.view(np.int16).copy()).view(torch.bfloat16).to(DEV)  # noqa: E731
+        else:
+            conv = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)  # noqa: E731
+        x, g, bounds, levels = (conv(case[k]) for k in ('x', 'g', 'bounds', 'levels'))
+        y, state = torch.ops.fewbit.quantize(x, bounds)
+        gin = torch.ops.fewbit.quantize_backward(g, state, levels)
+        assert y.data_ptr() != x.data_ptr()                     # out of place, as in the reference
+        assert np.array_equal(state.cpu().numpy(), case['state']), case['key']
+        raw = gin.cpu().view(torch.int16).numpy() if case['bf16'] else gin.cpu().numpy()
+        assert np.array_equal(raw.view(np.uint8), case['gin'].view(np.uint8)), case['key']
+
+
+def test_errors_are_loud():
+    x = torch.randn(64, device=DEV)
+    bounds, levels = (t.contiguous() for t in store.get('gelu', 3, DEV, torch.float32))
+    bounds = bounds[1:-1].contiguous()
+    with pytest.raises(RuntimeError, match='contiguous'):
+        torch.ops.fewbit.relu(torch.randn(8, 8, device=DEV).t())
+    with pytest.raises(RuntimeError, match='float32 or bfloat16'):
+        torch.ops.fewbit.relu(x.double())
+    with pytest.raises(RuntimeError, match='float32 or bfloat16'):
+        torch.ops.fewbit.gelu(x.half(), bounds, levels)
+    with pytest.raises(RuntimeError, match='lesser than size'):
+        torch.ops.fewbit.gelu(x.clone(), bounds[:-1], levels)
+    with pytest.raises(RuntimeError, match='256'):
+        torch.ops.fewbit.gelu(x.clone(), torch.zeros(256, device=DEV), torch.zeros(257, device=DEV))
+    with pytest.raises(RuntimeError):                           # in-place on a leaf that needs grad
+        FF.gelu(torch.randn(8, device=DEV, requires_grad=True), bits=3)
+    with pytest.raises(NotImplementedError):
+        torch.ops.fewbit.stepwise(x.clone(), bounds, levels)
+
+
+def test_modules_and_piecewise_modules_on_cuda():
+    x = torch.linspace(-7, 7, 1001, device=DEV)
+    for cls, ref, args in ((fewbit.ReLU, F.relu, ()), (fewbit.ReLU6, F.relu6, ()),
+                           (fewbit.LeakyReLU, F.leaky_relu, (0.2, )),
+                           (fewbit.Hardtanh, F.hardtanh, (-2.0, 2.0)),
+                           (fewbit.Hardsigmoid, F.hardsigmoid, ()),
+                           (fewbit.Threshold, F.threshold, (1.0, 3.0))):
+        h = x.clone().requires_grad_()
+        y = cls(*args)(h + 0)                                   # reference bug C-5: modules work
+        assert torch.allclose(y, ref(x, *args), atol=1e-6), cls.__name__
+        y.sum().backward()
+        p = x.clone().requires_grad_()
+        ref(p, *args).sum().backward()
+        same = x != 0 if cls is fewbit.LeakyReLU else torch.ones_like(x, dtype=torch.bool)
+        assert torch.allclose(h.grad[same], p.grad[same], atol=1e-6), cls.__name__
+    assert torch.equal(fewbit.ReLU6()(torch.tensor([5.0, 6.0, 7.0], device=DEV)),
+                       torch.tensor([5.0, 6.0, 6.0], device=DEV))          # C-6: saturates at 6
+    for bits in (1, 2, 3, 4):
+        m = fewbit.SiLU(bits=bits)
+        h = x.clone().requires_grad_()
+        m(h + 0).sum().backward()
+        borders, levels = store.get('silu', bits, DEV, torch.float32)
+        assert torch.equal(h.grad, levels[torch.searchsorted(borders[1:-1].contiguous(), x)])
+
+
+def test_runs_on_the_current_stream_and_shapes():
+    side = torch.cuda.Stream()
+    x = (torch.randn(8, 128, 768, device=DEV) * 2)
+    with torch.cuda.stream(side):
+        h = x.clone().requires_grad_()
+        y = FF.mish(h * 1, bits=4)
+        y.backward(torch.ones_like(y))
+    side.synchronize()
+    assert y.shape == x.shape and h.grad.shape == x.shape
+    borders, levels = store.get('mish', 4, DEV, torch.float32)
+    assert torch.equal(h.grad, levels[torch.searchsorted(borders[1:-1].contiguous(), x)])
+    z = FF.relu(torch.empty(0, 3, device=DEV))                  # empty tensors are fine
+    assert z.shape == (0, 3)
+
+
+def test_oracle_agrees_through_the_operator_path():
+    torch.manual_seed(5)
+    x = (torch.randn(70001, device=DEV) * 2).to(torch.bfloat16)
+    g = torch.randn(70001, device=DEV).to(torch.bfloat16)
+    borders, levels = store.get('tanh', 4, DEV, torch.bfloat16)
+    h = x.clone().requires_grad_()
+    FF.tanh(h + 0, bits=4).backward(g)
+    bits16 = lambda t: t.detach().cpu().contiguous().view(torch.int16).numpy().view(np.uint16)  # noqa: E731
+    _, state = oracle.stepwise_forward('tanh', bits16(x), bits16(borders[1:-1]), 4)
+    want = oracle.stepwise_backward(state, bits16(g), bits16(levels), 4)
+    assert np.array_equal(bits16(h.grad), want)
+
+
+def test_randomized_linear_on_cuda():
+    torch.manual_seed(42)
+    layer = fewbit.RandomizedLinear(256, 128, proj_dim=64).to(DEV)
+    ref = torch.nn.Linear(256, 128).to(DEV)
+    ref.load_state_dict(layer.state_dict())
+    x = torch.randn(512, 256, device=DEV, requires_grad=True)
+    acc = torch.zeros_like(layer.weight)
+    for _ in range(1024):
+        layer.zero_grad()
+        x.grad = None
+        y = layer(x)
+        y.backward(torch.ones_like(y))
+        acc += layer.weight.grad
+    gi = x.grad.clone()
+    x.grad = None
+    z = ref(x)
+    z.backward(torch.ones_like(z))
+    assert (torch.linalg.norm(y - z) / torch.linalg.norm(z)).item() < 1e-5
+    assert (torch.linalg.norm(gi - x.grad) / torch.linalg.norm(x.grad)).item() < 1e-5
+    err = torch.linalg.norm(acc / 1024 - ref.weight.grad) / torch.linalg.norm(ref.weight.grad)
+    assert err.item() < 0.1                                      # linear_test.py:88-89
+    # fresh randomness per call on CUDA (reference bug C-9: same S every call)
+    layer.zero_grad(); layer(x).sum().backward(); a = layer.weight.grad.clone()
+    layer.zero_grad(); layer(x).sum().backward()
+    assert not torch.equal(a, layer.weight.grad)

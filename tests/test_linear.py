@@ -1,0 +1,106 @@
+"""RandomizedLinear (LinearGRP): bit-exact against the reference on CPU for the same seed, and
+the reference's own statistical test (fewbit/modules/linear_test.py:57-92)."""
+import pytest
+import torch
+
+import fewbit_b200 as fewbit
+from fewbit_b200.functional.linear import calc_proj_dim
+
+
+@pytest.mark.parametrize('kind', ['gaussian', 'rademacher'])
+@pytest.mark.parametrize('bias', [False, True])
+def test_bit_exact_with_reference_on_cpu(golden_linear, kind, bias):
+    """Same seed -> same sketch -> same y / grad_input / grad_weight / grad_bias as
+    LinearGRPFunc of the reference (tests/golden/make_golden.py ran it)."""
+    key = f'{kind}-{int(bias)}'
+    g = {k.split('/', 1)[1]: torch.from_numpy(v) for k, v in golden_linear.items()
+         if k.startswith(key + '/')}
+    layer = fewbit.LinearGRP(24, 12, bias, proj_dim=16, matmul=kind)
+    with torch.no_grad():
+        layer.weight.copy_(g['weight'])
+        if bias:
+            layer.bias.copy_(g['bias'])
+    x = g['x'].clone().requires_grad_()
+    torch.manual_seed(1234)
+    y = layer(x)
+    y.backward(g['gy'])
+    torch.testing.assert_close(y.detach(), g['y'], rtol=0, atol=0)
+    torch.testing.assert_close(x.grad, g['grad_input'], rtol=0, atol=0)
+    torch.testing.assert_close(layer.weight.grad, g['grad_weight'], rtol=0, atol=0)
+    if bias:
+        torch.testing.assert_close(layer.bias.grad, g['grad_bias'], rtol=0, atol=0)
+
+
+def test_proj_dim_rules():
+    # reference functional/linear.py:17-24, 72-81: proj_dim wins, then int(ratio*N), then N;
+    # falsy clamps are ignored.
+    assert calc_proj_dim(16384, 0.2, None, None, 3) == 3276
+    assert calc_proj_dim(100, 0.2, 64, None, None) == 64
+    assert calc_proj_dim(100, None, None, None, None) == 100
+    assert calc_proj_dim(10, 0.2, None, None, 3) == 3
+    assert calc_proj_dim(1000, 0.5, None, 128, None) == 128
+    assert calc_proj_dim(1000, 0.5, None, 0, 0) == 500
+    layer = fewbit.LinearGRP(4, 4)
+    with pytest.raises(ValueError):
+        layer(torch.randn(8, 4))                      # neither proj_dim nor ratio
+    with pytest.raises(ValueError):
+        fewbit.LinearGRP(4, 4, proj_dim=2, proj_dim_min=-1)(torch.randn(8, 4))
+    with pytest.raises(ValueError):
+        fewbit.LinearGRP(4, 4, proj_dim=2, proj_dim_min=5, proj_dim_max=3)(torch.randn(8, 4))
+    with pytest.raises(NotImplementedError):
+        fewbit.LinearGRP(4, 4, proj_dim=2, matmul='dct')(torch.randn(8, 4))
+
+
+def test_forward_is_exact():
+    # linear_test.py:57-69
+    torch.manual_seed(42)
+    for bias in (False, True):
+        layer = fewbit.LinearGRP(8, 4, bias, proj_dim=64)
+        ref = torch.nn.Linear(8, 4, bias)
+        ref.load_state_dict(layer.state_dict())
+        x = torch.randn(128, 8)
+        with torch.no_grad():
+            rel = torch.linalg.norm(ref(x) - layer(x)) / torch.linalg.norm(ref(x))
+        assert rel.item() < 1e-6
+
+
+@pytest.mark.parametrize('kind', ['gaussian', 'rademacher'])
+def test_weight_gradient_is_unbiased(kind):
+    # linear_test.py:71-92 with fewer repeats (512 instead of 2048) and a matching bound:
+    # grad_input / grad_bias exact, grad_weight within 0.2 relative error of the mean.
+    torch.manual_seed(42)
+    layer = fewbit.LinearGRP(256, 128, True, proj_dim=64, matmul=kind)
+    ref = torch.nn.Linear(256, 128, True)
+    ref.load_state_dict(layer.state_dict())
+    x = torch.randn(512, 256, requires_grad=True)
+    acc = torch.zeros_like(layer.weight)
+    repeats = 512
+    for _ in range(repeats):
+        layer.zero_grad()
+        x.grad = None
+        y = layer(x)
+        y.backward(torch.ones_like(y))
+        acc += layer.weight.grad
+    gi, gb = x.grad.clone(), layer.bias.grad.clone()
+    x.grad = None
+    z = ref(x)
+    z.backward(torch.ones_like(z))
+    assert (torch.linalg.norm(gi - x.grad) / torch.linalg.norm(x.grad)).item() < 1e-6
+    assert (torch.linalg.norm(gb - ref.bias.grad) / torch.linalg.norm(ref.bias.grad)).item() < 1e-6
+    err = torch.linalg.norm(acc / repeats - ref.weight.grad) / torch.linalg.norm(ref.weight.grad)
+    assert err.item() < 0.2
+
+
+def test_user_generator_is_honoured_and_replayed():
+    layer = fewbit.LinearGRP(16, 8, proj_dim=8, generator=torch.Generator().manual_seed(7))
+    x = torch.randn(32, 16)
+    grads = []
+    for _ in range(2):
+        layer.generator.manual_seed(7)
+        layer.zero_grad()
+        layer(x).sum().backward()
+        grads.append(layer.weight.grad.clone())
+    torch.testing.assert_close(grads[0], grads[1], rtol=0, atol=0)
+    layer.zero_grad()
+    layer(x).sum().backward()                        # generator advanced: a different sketch
+    assert not torch.equal(layer.weight.grad, grads[0])
