@@ -1,0 +1,42 @@
+"""Launch each hot kernel a few times at benchmark size -- the target of the ncu captures
+(`ncu --set full -k regex:tiles_kernel ... python benchmarks/profile_kernels.py`)."""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from fewbit_b200 import native  # noqa: E402
+from fewbit_b200.functional import store  # noqa: E402
+
+dev = torch.device('cuda:0')
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+which = sys.argv[2] if len(sys.argv) > 2 else 'all'
+torch.manual_seed(0)
+
+if which in ('all', 'mask'):
+    n = 1 << 29
+    x = torch.empty(n, dtype=torch.bfloat16, device=dev).normal_(0, 2)
+    g = torch.empty(n, dtype=torch.bfloat16, device=dev).normal_()
+    y, gin = torch.empty_like(x), torch.empty_like(g)
+    state = native.new_state(x, 1)
+    for _ in range(reps):
+        native.piecewise_forward('relu', x, y, state)
+        native.piecewise_backward('relu', state, g, gin)
+    torch.cuda.synchronize()
+    del x, g, y, gin, state
+
+if which in ('all', 'gelu'):
+    n = 128 * 128 * 3072
+    for dtype in (torch.float32, torch.bfloat16):
+        borders, levels = store.get('gelu', 3, dev, dtype)
+        bounds = borders[1:-1].contiguous()
+        x = (torch.randn(n, device=dev) * 2).to(dtype)
+        g = torch.randn(n, device=dev).to(dtype)
+        y, gin = torch.empty_like(x), torch.empty_like(g)
+        state = native.new_state(x, 3)
+        for _ in range(reps):
+            native.stepwise_forward('gelu', x, y, state, 3, bounds)
+            native.stepwise_backward(state, g, gin, 3, levels)
+        torch.cuda.synchronize()
+print('done')

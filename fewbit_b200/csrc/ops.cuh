@@ -3,6 +3,8 @@
 
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "tile.cuh"
 
 namespace fewbit {
@@ -16,14 +18,20 @@ struct NoScratch {
 // reference BinarySearch fewbit/cuda/codec.cu:118-131).  NaN -> 0 because every
 // comparison is false, exactly as in the reference CUDA kernel.
 //
-//  B <= 3 : the (<= 7) bounds live in registers; a compare/select tree, B compares.
-//  B >= 4 : bounds in shared memory; branch-free binary search, B-1 dependent LDS
-//           (the first probe is a register).  For B >= 6 the table is skewed by one word
-//           per 32 entries so that the 2^k probes of level k fall into distinct banks.
+//  B <= 2 : the (<= 3) bounds live in registers; a compare/select tree, B compares.
+//  B >= 3 : cell look-up.  The kernels are bound by the ALU pipe (FSETP/FSEL/LOP3), not by
+//           HBM, so the search is moved off it: a monotone map  cell(x) = round(sat(x*s + o)
+//           * (C-1))  (two FFMAs on the FMA pipe) indexes a C = 128..2048 entry shared-memory
+//           table holding  k = #{ i : cell(bounds[i]) < cell }.  Because cell() is monotone,
+//           bounds in earlier cells are < x and bounds in later cells are > x, so
+//           code(x) = k + (bounds[k] < x)  -- one gather, one compare -- whenever at most one
+//           bound falls into x's cell.  Cells holding two or more bounds are flagged and
+//           resolved by an exact branch-free binary search (never taken for the built-in
+//           tables or make_table(): 1024 cells already separate all of their bounds).
 // Tables shorter than 2^B - 1 are padded with +inf (never counted).
 // =====================================================================================
 
-template <typename T, int B, bool kInRegisters = (B <= 3)> struct Bucketizer;
+template <typename T, int B, bool kInRegisters = (B <= 2)> struct Bucketizer;
 
 template <typename T, int B> struct Bucketizer<T, B, true> {
     static constexpr int kCount = (1 << B) - 1;
@@ -38,56 +46,131 @@ template <typename T, int B> struct Bucketizer<T, B, true> {
             b[i] = i < nbounds ? to_float<T>(bounds[i]) : CUDART_INF_F;
     }
 
-    __device__ __forceinline__ uint32_t operator()(float x) const {
-        if constexpr (B == 1) {
-            return b[0] < x ? 1u : 0u;
-        } else if constexpr (B == 2) {
-            const bool p1 = b[1] < x;
-            const bool p2 = (p1 ? b[2] : b[0]) < x;
-            return (p1 ? 2u : 0u) | (p2 ? 1u : 0u);
-        } else {
-            const bool p1 = b[3] < x;
-            const bool p2 = (p1 ? b[5] : b[1]) < x;
-            const float lo = p2 ? b[2] : b[0];
-            const float hi = p2 ? b[6] : b[4];
-            const bool p3 = (p1 ? hi : lo) < x;
-            return (p1 ? 4u : 0u) | (p2 ? 2u : 0u) | (p3 ? 1u : 0u);
+    __device__ __forceinline__ void lookup(const float (&x)[8], uint32_t (&code)[8]) const {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if constexpr (B == 1) {
+                code[j] = b[0] < x[j] ? 1u : 0u;
+            } else {
+                const bool p1 = b[1] < x[j];
+                const bool p2 = (p1 ? b[2] : b[0]) < x[j];
+                code[j] = (p1 ? 2u : 0u) | (p2 ? 1u : 0u);
+            }
         }
     }
 };
 
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
 template <typename T, int B> struct Bucketizer<T, B, false> {
-    static constexpr int kCount = (1 << B) - 1;
-    static constexpr bool kSkew = B >= 6;
-    static constexpr int skew(int i) { return kSkew ? i + (i >> 5) : i; }
+    static constexpr int kSize = 1 << B;  // bounds padded with +inf to a power of two
+    // Cells: enough to separate the borders of every shipped table, few enough that the
+    // gather stays (nearly) bank-conflict free: 128 one-byte entries = 32 words = 1 per bank.
+    static constexpr int kCells = B == 3 ? 128 : B == 4 ? 256 : B == 5 ? 512 : 2048;
+    static constexpr bool kByteEntries = B <= 7;  // k <= 127 leaves bit 7 for the flag
+    using Entry = typename std::conditional<kByteEntries, uint8_t, uint16_t>::type;
+    static constexpr uint32_t kCrowded = kByteEntries ? 0x80u : 0x8000u;
     struct Scratch {
-        float table[skew(kCount) + 1];
+        float bounds[256];  // index = entry (flag included) must stay inside the array
+        uint16_t bound_cell[kSize];
+        alignas(4) Entry lut[kCells];
     };
     const T *bounds;
     int nbounds;
+    float scale, offset;
+    float lut_base;       // shared-space byte address of lut[], as the bits of a denormal float
+    uint32_t table_base;  // shared-space byte address of bounds[]
     const float *table;
-    float top;
 
-    __device__ __forceinline__ void prepare(Scratch &s) {
-        for (int i = threadIdx.x; i < kCount; i += blockDim.x)
-            s.table[skew(i)] = i < nbounds ? to_float<T>(bounds[i]) : CUDART_INF_F;
-        __syncthreads();
-        table = s.table;
-        top = s.table[skew(kCount / 2)];
+    // Shared-memory address of x's LUT entry, computed entirely on the FMA pipe: sat() clamps
+    // (and sends NaN to 0); the second FMA works in the denormal range, where the bit pattern
+    // of a float *is* its value in units of 2^-149, so  bits = round(t * (C-1)) * stride + base.
+    __device__ __forceinline__ uint32_t entry_address(float x) const {
+        const float t = __saturatef(fmaf(x, scale, offset));
+        return __float_as_uint(fmaf(t, __uint_as_float((uint32_t)(kCells - 1)), lut_base));
+    }
+    __device__ __forceinline__ uint32_t cell_of(float x) const {
+        return entry_address(x) - __float_as_uint(lut_base);
     }
 
-    __device__ __forceinline__ uint32_t operator()(float x) const {
-        constexpr int kTopStep = 1 << (B - 1);
-        // `pos` is skew(idx) where idx counts the bounds known to be < x.
-        int pos = top < x ? skew(kTopStep) : 0;
-#pragma unroll
-        for (int step = kTopStep >> 1; step >= 1; step >>= 1) {
-            // probe entry idx + step - 1; its skewed address is pos + skew(step - 1), and
-            // accepting it advances pos by skew(step) ("bank-skewed search").
-            if (table[pos + skew(step - 1)] < x) pos += skew(step);
+    __device__ __forceinline__ void prepare(Scratch &s) {
+        const float lo = nbounds > 0 ? to_float<T>(bounds[0]) : 0.0f;
+        const float hi = nbounds > 0 ? to_float<T>(bounds[nbounds - 1]) : 0.0f;
+        const float span = hi - lo;
+        if (span > 0.0f && span < CUDART_INF_F) {
+            scale = 1.0f / span;
+            offset = -lo * scale;
+        } else {  // a single (or degenerate) border: any monotone map will do
+            scale = 1.0f;
+            offset = 0.5f - lo;
         }
-        if constexpr (kSkew) pos -= (pos * 1986) >> 16;  // pos - pos / 33, valid for pos <= 262
-        return (uint32_t)pos;
+        if (!(fabsf(offset) < CUDART_INF_F)) offset = 0.5f;
+        lut_base = __uint_as_float((uint32_t)__cvta_generic_to_shared(s.lut));
+        table_base = (uint32_t)__cvta_generic_to_shared(s.bounds);
+        table = s.bounds;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+            const float v = i < nbounds ? to_float<T>(bounds[i]) : CUDART_INF_F;
+            s.bounds[i] = v;
+            if (i < kSize) s.bound_cell[i] = i < nbounds ? (uint16_t)cell_of(v) : (uint16_t)kCells;
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < kCells; c += blockDim.x) {
+            int k = 0;  // first bound whose cell is >= c
+#pragma unroll
+            for (int step = kSize >> 1; step >= 1; step >>= 1)
+                if (s.bound_cell[k + step - 1] < c) k += step;
+            const bool crowded = k + 1 < kSize && s.bound_cell[k + 1] == c;
+            s.lut[c] = (Entry)(k | (crowded ? kCrowded : 0u));
+        }
+        __syncthreads();
+    }
+
+    // Exact branch-free binary search; out of line on purpose (rare, keeps the hot loop small).
+    static __device__ __noinline__ uint32_t exact(const float *sorted, float x) {
+        int k = 0;
+#pragma unroll
+        for (int step = kSize >> 1; step >= 1; step >>= 1)
+            if (sorted[k + step - 1] < x) k += step;
+        return (uint32_t)k;
+    }
+
+    __device__ __forceinline__ void lookup(const float (&x)[8], uint32_t (&code)[8]) const {
+        uint32_t entry[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if constexpr (kByteEntries) {
+                entry[j] = lds_u8(entry_address(x[j]));
+            } else {
+                const uint32_t base = __float_as_uint(lut_base);
+                entry[j] = lds_u16(base + 2 * (entry_address(x[j]) - base));
+            }
+        }
+        const uint32_t any = (entry[0] | entry[1] | entry[2]) | (entry[3] | entry[4] | entry[5]) |
+                             (entry[6] | entry[7]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t slot = kByteEntries ? entry[j] : (entry[j] & 0xffu);
+            code[j] = entry[j] + (lds_f32(table_base + 4 * slot) < x[j] ? 1u : 0u);
+        }
+        if (any & kCrowded) {  // some cell holds several bounds: resolve those exactly
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (entry[j] & kCrowded) code[j] = exact(table, x[j]);
+        }
     }
 };
 
@@ -100,7 +183,7 @@ template <typename T, int B> struct Bucketizer<T, B, false> {
 
 struct EluFamily {  // celu / elu / selu:  x > 0 ? x*pos : expm1(x*in_scale)*neg
     float pos, neg, in_scale;
-    __device__ __forceinline__ float operator()(float x) const {
+    template <typename T> __device__ __forceinline__ float eval(float x) const {
         return x > 0.0f ? x * pos : expm1f(x * in_scale) * neg;
     }
 };
@@ -117,71 +200,113 @@ struct SeluFn : EluFamily {  // codec.cu:588-600
                         (float)1.0507009873554804934193349852946,
                     1.0f} {}
 };
-struct GeluFn {  // codec.cu:539-544 (x * normcdf(x)); ATen: x * 0.5 * (1 + erf(x / sqrt(2)))
+// GELU.  ATen evaluates  (0.5 x) * (1 + erf(x / sqrt 2))  with libdevice erff, a two-branch
+// routine that costs ~9 ALU-pipe selects per element.  Here erf comes from one branch-free
+// evaluation of erfc:   erfc(t) = s * 2^(P(s) - log2(e) t^2),  s = 1 / (1 + t/2),  t = |x|/sqrt 2
+// (P fitted by tools/fit_gelu.py; degree 9 keeps erf within one fp32 ulp-of-one, degree 5 is
+// enough for a bf16 result), then  erf = copysign(1 - erfc, x)  and ATen's last two steps
+// verbatim, so rounding and the 1+erf cancellation in the negative tail behave like F.gelu.
+// 12 FMA-pipe ops + 2 MUFU + 1 ALU op instead of ~33 instructions.
+__device__ __forceinline__ float rcp_approx(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+struct GeluFn {  // codec.cu:539-544 (x * normcdf(x))
     __host__ GeluFn(double, double) {}
-    __device__ __forceinline__ float operator()(float x) const {
-        return (x * 0.5f) * (1.0f + erff(x * 0.70710678118654752440f));
+    template <typename T> __device__ __forceinline__ float eval(float x) const {
+        const float t = fabsf(x) * 0.70710678118654752440f;
+        const float s = rcp_approx(fmaf(t, 0.5f, 1.0f));
+        float p;
+        if constexpr (sizeof(T) == 2) {
+            p = 2.816799879e-01f;
+            p = fmaf(p, s, -8.819190860e-01f);
+            p = fmaf(p, s, 5.309718251e-01f);
+            p = fmaf(p, s, 4.433360100e-01f);
+            p = fmaf(p, s, 1.451876998e+00f);
+            p = fmaf(p, s, -1.825967312e+00f);
+        } else {
+            p = 2.534233928e-01f;
+            p = fmaf(p, s, -1.219192386e+00f);
+            p = fmaf(p, s, 2.214311123e+00f);
+            p = fmaf(p, s, -1.711810946e+00f);
+            p = fmaf(p, s, 4.512821436e-01f);
+            p = fmaf(p, s, -2.884398699e-01f);
+            p = fmaf(p, s, 1.443251818e-01f);
+            p = fmaf(p, s, 5.390827656e-01f);
+            p = fmaf(p, s, 1.442767620e+00f);
+            p = fmaf(p, s, -1.825749040e+00f);
+        }
+        const float erfc_t = s * ex2_approx(fmaf(t * -1.4426950408889634f, t, p));
+        const float erf_x = copysignf(1.0f - erfc_t, x);
+        return (x * 0.5f) * (1.0f + erf_x);
     }
 };
 struct HardswishFn {  // codec.cu:546-564
     __host__ HardswishFn(double, double) {}
-    __device__ __forceinline__ float operator()(float x) const {
+    template <typename T> __device__ __forceinline__ float eval(float x) const {
         return x * fminf(fmaxf(x + 3.0f, 0.0f), 6.0f) * (1.0f / 6.0f);
     }
 };
 struct LogSigmoidFn {  // codec.cu:566-576
     __host__ LogSigmoidFn(double, double) {}
-    __device__ __forceinline__ float operator()(float x) const {
+    template <typename T> __device__ __forceinline__ float eval(float x) const {
         return fminf(0.0f, x) - log1pf(expf(-fabsf(x)));
     }
 };
 struct MishFn {  // codec.cu:578-586
     __host__ MishFn(double, double) {}
-    __device__ __forceinline__ float operator()(float x) const {
+    template <typename T> __device__ __forceinline__ float eval(float x) const {
         return x * tanhf(log1pf(expf(x)));
     }
 };
 struct SigmoidFn {  // codec.cu:602-607
     __host__ SigmoidFn(double, double) {}
-    __device__ __forceinline__ float operator()(float x) const {
+    template <typename T> __device__ __forceinline__ float eval(float x) const {
         return 1.0f / (1.0f + expf(-x));
     }
 };
 struct SiluFn {  // codec.cu:609-614
     __host__ SiluFn(double, double) {}
-    __device__ __forceinline__ float operator()(float x) const { return x / (1.0f + expf(-x)); }
+    template <typename T> __device__ __forceinline__ float eval(float x) const { return x / (1.0f + expf(-x)); }
 };
 struct SoftplusFn {  // codec.cu:616-632
     float beta, threshold;
     __host__ SoftplusFn(double b, double t) : beta((float)b), threshold((float)t) {}
-    __device__ __forceinline__ float operator()(float x) const {
+    template <typename T> __device__ __forceinline__ float eval(float x) const {
         const float bx = x * beta;
         return bx > threshold ? x : log1pf(expf(bx)) / beta;
     }
 };
 struct SoftsignFn {  // codec.cu:634-639
     __host__ SoftsignFn(double, double) {}
-    __device__ __forceinline__ float operator()(float x) const { return x / (1.0f + fabsf(x)); }
+    template <typename T> __device__ __forceinline__ float eval(float x) const { return x / (1.0f + fabsf(x)); }
 };
 struct TanhFn {  // codec.cu:641-646
     __host__ TanhFn(double, double) {}
-    __device__ __forceinline__ float operator()(float x) const { return tanhf(x); }
+    template <typename T> __device__ __forceinline__ float eval(float x) const { return tanhf(x); }
 };
 struct TanhshrinkFn {  // codec.cu:648-653
     __host__ TanhshrinkFn(double, double) {}
-    __device__ __forceinline__ float operator()(float x) const { return x - tanhf(x); }
+    template <typename T> __device__ __forceinline__ float eval(float x) const { return x - tanhf(x); }
 };
 
-// Forward op of a continuous activation: y = fn(x), code = bucket(x).
+// Forward op of a continuous activation: y = fn(x), code = bucket(x), eight values at a time.
 template <class Fn, typename T, int B> struct QuantizeOp {
     static constexpr int kBits = B;
     using Scratch = typename Bucketizer<T, B>::Scratch;
     Fn fn;
     Bucketizer<T, B> bucket;
     __device__ __forceinline__ void prepare(Scratch &s) { bucket.prepare(s); }
-    __device__ __forceinline__ float apply(float x, uint32_t &code) const {
-        code = bucket(x);
-        return fn(x);
+    __device__ __forceinline__ void apply(float (&v)[8], uint32_t (&code)[8]) const {
+        bucket.lookup(v, code);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fn.template eval<T>(v[j]);
     }
 };
 
@@ -285,7 +410,10 @@ template <class Fn> struct MaskOp {
     using Scratch = NoScratch;
     Fn fn;
     __device__ __forceinline__ void prepare(Scratch &) {}
-    __device__ __forceinline__ float apply(float x, uint32_t &code) const { return fn(x, code); }
+    __device__ __forceinline__ void apply(float (&v)[8], uint32_t (&code)[8]) const {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fn(v[j], code[j]);
+    }
 };
 
 // Backward of the 1-bit family: factor = mask ? on : off  (codec.cu:271-296: idx * g;

@@ -124,31 +124,33 @@ template <int B> __device__ __forceinline__ void put_octet(uint8_t *p, uint64_t 
 
 // Forward: turn this lane's 8 codes of one subtile into its octet and park it in the strip.
 //   code[j] belongs to v[j] of Subtile<T>.
+// Four codes -> one 4*B-bit field.  Written as multiply-adds so that the shifts can go to the
+// FMA pipe (IMAD) instead of the ALU pipe, which is the busy one in the forward kernels.
+template <int B>
+__device__ __forceinline__ uint32_t pack4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+    return c0 + c1 * (1u << B) + c2 * (1u << (2 * B)) + c3 * (1u << (3 * B));
+}
+
 template <typename T, int B>
 __device__ __forceinline__ void stage_codes(uint8_t *strip, int lane, const uint32_t (&code)[8]) {
+    const uint32_t first = pack4<B>(code[0], code[1], code[2], code[3]);
+    const uint32_t second = pack4<B>(code[4], code[5], code[6], code[7]);
     if constexpr (sizeof(T) == 2) {
-        uint64_t octet = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) octet |= (uint64_t)code[j] << (B * j);
+        // bf16: the lane's 8 values are one octet.
+        const uint64_t octet = B <= 4 ? (uint64_t)(first | (second << ((4 * B) & 31)))
+                                      : ((uint64_t)first | ((uint64_t)second << (4 * B)));
         put_octet<B>(strip + B * lane, octet);
     } else {
-        // lane l holds the low half (4 codes) of octet l/2 ... for even/odd pairing see below:
-        //   elements [4l, 4l+4)       -> half (l & 1) of octet  l >> 1
-        //   elements [128+4l, 128+4l+4) -> half (l & 1) of octet 16 + (l >> 1)
-        uint32_t first = 0, second = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            first |= code[j] << (B * j);
-            second |= code[4 + j] << (B * j);
-        }
-        // Even lanes assemble octet l>>1 (need the odd neighbour's `first`), odd lanes
-        // assemble octet 16 + (l>>1) (need the even neighbour's `second`): one shuffle.
+        // fp32: elements [4l, 4l+4) are half (l & 1) of octet l >> 1, elements
+        // [128+4l, 128+4l+4) are half (l & 1) of octet 16 + (l >> 1).  Even lanes assemble
+        // octet l>>1 (they need the odd neighbour's `first`), odd lanes assemble octet
+        // 16 + (l>>1) (they need the even neighbour's `second`): one shuffle.
         const bool odd = lane & 1;
-        uint32_t theirs = __shfl_xor_sync(0xffffffffu, odd ? first : second, 1);
-        uint64_t octet = odd ? ((uint64_t)theirs | ((uint64_t)second << (4 * B)))
-                             : ((uint64_t)first | ((uint64_t)theirs << (4 * B)));
-        int index = (lane >> 1) + (odd ? 16 : 0);
-        put_octet<B>(strip + B * index, octet);
+        const uint32_t theirs = __shfl_xor_sync(0xffffffffu, odd ? first : second, 1);
+        const uint32_t low = odd ? theirs : first, high = odd ? second : theirs;
+        const uint64_t octet = B <= 4 ? (uint64_t)(low | (high << ((4 * B) & 31)))
+                                      : ((uint64_t)low | ((uint64_t)high << (4 * B)));
+        put_octet<B>(strip + B * ((lane >> 1) + (odd ? 16 : 0)), octet);
     }
 }
 
@@ -190,7 +192,7 @@ __device__ __forceinline__ void fetch_codes(const uint32_t *strip, int lane, uin
 // Op concepts
 //   Forward op : static constexpr int kBits;
 //                __device__ void prepare(smem scratch)   (block-wide, before the loop)
-//                __device__ float apply(float x, uint32_t &code) const
+//                __device__ void apply(float (&v)[8], uint32_t (&code)[8]) const   v <- f(v)
 //   Backward op: static constexpr int kBits;
 //                __device__ void prepare(...)
 //                __device__ float factor(uint32_t code) const     gin = factor * gout
@@ -226,8 +228,7 @@ __global__ void __launch_bounds__(kThreads) forward_tiles_kernel(const T *x, T *
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             uint32_t code[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[u][j] = op.apply(v[u][j], code[j]);
+            op.apply(v[u], code);
             Subtile<T>::store(yt + u * kSubtile, lane, v[u]);
             stage_codes<T, B>(strip + u * subtile_bytes<B>(), lane, code);
         }
@@ -292,13 +293,16 @@ __global__ void __launch_bounds__(kThreads) forward_ragged_kernel(const T *x, T 
          o += (int64_t)gridDim.x * kThreads) {
         const int64_t e0 = first + 8 * o;
         uint64_t octet = 0;
+        float v[8];
+        uint32_t code[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = e0 + j < n ? to_float<T>(x[e0 + j]) : 0.0f;
+        op.apply(v, code);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (e0 + j < n) {
-                uint32_t code;
-                float r = op.apply(to_float<T>(x[e0 + j]), code);
-                y[e0 + j] = from_float<T>(r);
-                octet |= (uint64_t)code << (B * j);
+                y[e0 + j] = from_float<T>(v[j]);
+                octet |= (uint64_t)code[j] << (B * j);
             }
         }
         const int64_t b0 = (e0 / 8) * B;

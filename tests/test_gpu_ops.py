@@ -76,11 +76,15 @@ def test_forward_matches_torch_cuda_kernels(name, dtype):
     torch.manual_seed(11)
     x = (torch.randn(1 << 20, device=DEV) * 2).to(dtype)
     args = {'celu': (1.5, ), 'elu': (0.7, ), 'softplus': (2.0, 10.0)}.get(name, ())
-    ref = (getattr(F, name, None) or getattr(torch, name))(x, *args)
+    # Yardstick: the ATen CUDA kernel in fp32 opmath, rounded once.  (In bf16 torch evaluates
+    # the composites softsign / tanhshrink step by step in bf16, which is less accurate than
+    # one fp32 evaluation + one rounding -- what ATen's fused kernels and ours do.)
+    ref = (getattr(F, name, None) or getattr(torch, name))(x.float(), *args)
     y = getattr(FF, name)(x.clone(), *args, bits=2)
     if dtype == torch.float32:
         tol = 4 * (torch.nextafter(ref.abs(), ref.abs() + 1) - ref.abs()) + 2.5e-7
     else:
+        ref = ref.to(dtype)
         tol = ref.float().abs() * 2.0 ** -7 + 1e-6
     err = (y.float() - ref.float()).abs()
     assert torch.all(err <= tol), f'{name}: max err {err.max().item():.3e}'
