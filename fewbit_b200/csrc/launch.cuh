@@ -6,11 +6,30 @@
 
 #include "ops.cuh"
 
-#ifndef FEWBIT_U_F32
-#define FEWBIT_U_F32 2  // subtiles per warp tile, fp32: 4 LDG.128 in flight per lane
+// Tile configuration per kernel class, from the sweep in profiles/r01_tuning_sweep.md
+// (B200, GB/s of algorithmic bytes; torch's copy kernel reaches 6520 on the same box):
+//   light kernels (1-bit masks, every backward): two LDG.128 in flight per lane and no register
+//     cap -> 6.2-6.3 TB/s; four loads or a tighter register budget cost 5-7 %.
+//   math-heavy forward kernels (continuous activations): U = 4 subtiles per warp tile with a
+//     64 (bf16) / 80 (fp32) register budget.
+// Overridable per build for further sweeps.
+#ifndef FEWBIT_U_LIGHT_F32
+#define FEWBIT_U_LIGHT_F32 1
 #endif
-#ifndef FEWBIT_U_BF16
-#define FEWBIT_U_BF16 4  // bf16: 4 LDG.128 in flight per lane
+#ifndef FEWBIT_U_LIGHT_BF16
+#define FEWBIT_U_LIGHT_BF16 2
+#endif
+#ifndef FEWBIT_U_HEAVY
+#define FEWBIT_U_HEAVY 4
+#endif
+#ifndef FEWBIT_MINB_LIGHT
+#define FEWBIT_MINB_LIGHT 1
+#endif
+#ifndef FEWBIT_MINB_HEAVY_F32
+#define FEWBIT_MINB_HEAVY_F32 3
+#endif
+#ifndef FEWBIT_MINB_HEAVY_BF16
+#define FEWBIT_MINB_HEAVY_BF16 4
 #endif
 
 namespace fewbit {
@@ -44,9 +63,13 @@ struct BackwardArgs {
 void note_launch();  // api.cu: bumps fewbit_launch_count()
 int sm_count();      // api.cu: SM count of the current device (cached per device)
 
-template <typename T> constexpr int tile_subtiles() {
-    return sizeof(T) == 2 ? FEWBIT_U_BF16 : FEWBIT_U_F32;
-}
+template <class Op, typename T> struct TileConfig {
+    static constexpr bool kHeavy = Op::kHeavy;
+    static constexpr int kSubtiles =
+        kHeavy ? FEWBIT_U_HEAVY : (sizeof(T) == 2 ? FEWBIT_U_LIGHT_BF16 : FEWBIT_U_LIGHT_F32);
+    static constexpr int kMinBlocks =
+        kHeavy ? (sizeof(T) == 2 ? FEWBIT_MINB_HEAVY_BF16 : FEWBIT_MINB_HEAVY_F32) : FEWBIT_MINB_LIGHT;
+};
 
 // Resident CTAs per SM for `kernel` (occupancy API, cached per instantiation), overridable
 // with FEWBIT_B200_CTAS_PER_SM for tuning runs.
@@ -75,12 +98,12 @@ template <typename T> bool vector_aligned(const void *a, const void *b, const vo
 template <class Op, typename T>
 cudaError_t launch_forward(const T *x, T *y, uint8_t *state, int64_t n, const Op &op,
                            cudaStream_t stream) {
-    constexpr int U = tile_subtiles<T>();
+    constexpr int U = TileConfig<Op, T>::kSubtiles;
     constexpr int64_t kTile = (int64_t)U * kSubtile;
     if (n <= 0) return cudaSuccess;
     const int64_t ntiles = vector_aligned<T>(x, y, state) ? n / kTile : 0;
     if (ntiles > 0) {
-        constexpr auto kernel = forward_tiles_kernel<Op, T, U>;
+        constexpr auto kernel = forward_tiles_kernel<Op, T, U, TileConfig<Op, T>::kMinBlocks>;
         const int64_t want = (ntiles + kWarps - 1) / kWarps;
         const int64_t cap = (int64_t)sm_count() * resident_ctas<kernel>();
         kernel<<<(unsigned)std::min(want, cap), kThreads, 0, stream>>>(x, y, state, ntiles, op);
@@ -101,12 +124,12 @@ cudaError_t launch_forward(const T *x, T *y, uint8_t *state, int64_t n, const Op
 template <class Op, typename T>
 cudaError_t launch_backward(const uint8_t *state, const T *gout, T *gin, int64_t n, const Op &op,
                             cudaStream_t stream) {
-    constexpr int U = tile_subtiles<T>();
+    constexpr int U = TileConfig<Op, T>::kSubtiles;
     constexpr int64_t kTile = (int64_t)U * kSubtile;
     if (n <= 0) return cudaSuccess;
     const int64_t ntiles = vector_aligned<T>(gout, gin, state) ? n / kTile : 0;
     if (ntiles > 0) {
-        constexpr auto kernel = backward_tiles_kernel<Op, T, U>;
+        constexpr auto kernel = backward_tiles_kernel<Op, T, U, TileConfig<Op, T>::kMinBlocks>;
         const int64_t want = (ntiles + kWarps - 1) / kWarps;
         const int64_t cap = (int64_t)sm_count() * resident_ctas<kernel>();
         kernel<<<(unsigned)std::min(want, cap), kThreads, 0, stream>>>(state, gout, gin, ntiles,

@@ -25,9 +25,9 @@ struct NoScratch {
 //           table holding  k = #{ i : cell(bounds[i]) < cell }.  Because cell() is monotone,
 //           bounds in earlier cells are < x and bounds in later cells are > x, so
 //           code(x) = k + (bounds[k] < x)  -- one gather, one compare -- whenever at most one
-//           bound falls into x's cell.  Cells holding two or more bounds are flagged and
-//           resolved by an exact branch-free binary search (never taken for the built-in
-//           tables or make_table(): 1024 cells already separate all of their bounds).
+//           bound falls into each cell.  If some cell holds two or more bounds the whole
+//           block falls back to an exact branch-free binary search (never the case for the
+//           built-in tables or make_table(), whose borders these cell counts separate).
 // Tables shorter than 2^B - 1 are padded with +inf (never counted).
 // =====================================================================================
 
@@ -81,13 +81,10 @@ template <typename T, int B> struct Bucketizer<T, B, false> {
     // Cells: enough to separate the borders of every shipped table, few enough that the
     // gather stays (nearly) bank-conflict free: 128 one-byte entries = 32 words = 1 per bank.
     static constexpr int kCells = B == 3 ? 128 : B == 4 ? 256 : B == 5 ? 512 : 2048;
-    static constexpr bool kByteEntries = B <= 7;  // k <= 127 leaves bit 7 for the flag
-    using Entry = typename std::conditional<kByteEntries, uint8_t, uint16_t>::type;
-    static constexpr uint32_t kCrowded = kByteEntries ? 0x80u : 0x8000u;
     struct Scratch {
-        float bounds[256];  // index = entry (flag included) must stay inside the array
+        float bounds[kSize];
         uint16_t bound_cell[kSize];
-        alignas(4) Entry lut[kCells];
+        alignas(4) uint8_t lut[kCells];
     };
     const T *bounds;
     int nbounds;
@@ -95,16 +92,14 @@ template <typename T, int B> struct Bucketizer<T, B, false> {
     float lut_base;       // shared-space byte address of lut[], as the bits of a denormal float
     uint32_t table_base;  // shared-space byte address of bounds[]
     const float *table;
+    bool crowded;         // some cell holds >= 2 borders: the whole block searches exactly
 
     // Shared-memory address of x's LUT entry, computed entirely on the FMA pipe: sat() clamps
     // (and sends NaN to 0); the second FMA works in the denormal range, where the bit pattern
-    // of a float *is* its value in units of 2^-149, so  bits = round(t * (C-1)) * stride + base.
+    // of a float *is* its value in units of 2^-149, so  bits = round(t * (C-1)) + base.
     __device__ __forceinline__ uint32_t entry_address(float x) const {
         const float t = __saturatef(fmaf(x, scale, offset));
         return __float_as_uint(fmaf(t, __uint_as_float((uint32_t)(kCells - 1)), lut_base));
-    }
-    __device__ __forceinline__ uint32_t cell_of(float x) const {
-        return entry_address(x) - __float_as_uint(lut_base);
     }
 
     __device__ __forceinline__ void prepare(Scratch &s) {
@@ -119,24 +114,26 @@ template <typename T, int B> struct Bucketizer<T, B, false> {
             offset = 0.5f - lo;
         }
         if (!(fabsf(offset) < CUDART_INF_F)) offset = 0.5f;
-        lut_base = __uint_as_float((uint32_t)__cvta_generic_to_shared(s.lut));
+        const uint32_t lut_address = (uint32_t)__cvta_generic_to_shared(s.lut);
+        lut_base = __uint_as_float(lut_address);
         table_base = (uint32_t)__cvta_generic_to_shared(s.bounds);
         table = s.bounds;
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        for (int i = threadIdx.x; i < kSize; i += blockDim.x) {
             const float v = i < nbounds ? to_float<T>(bounds[i]) : CUDART_INF_F;
             s.bounds[i] = v;
-            if (i < kSize) s.bound_cell[i] = i < nbounds ? (uint16_t)cell_of(v) : (uint16_t)kCells;
+            s.bound_cell[i] = i < nbounds ? (uint16_t)(entry_address(v) - lut_address) : (uint16_t)kCells;
         }
         __syncthreads();
+        int shared_cell = 0;
         for (int c = threadIdx.x; c < kCells; c += blockDim.x) {
             int k = 0;  // first bound whose cell is >= c
 #pragma unroll
             for (int step = kSize >> 1; step >= 1; step >>= 1)
                 if (s.bound_cell[k + step - 1] < c) k += step;
-            const bool crowded = k + 1 < kSize && s.bound_cell[k + 1] == c;
-            s.lut[c] = (Entry)(k | (crowded ? kCrowded : 0u));
+            shared_cell |= (k + 1 < kSize && s.bound_cell[k + 1] == c) ? 1 : 0;
+            s.lut[c] = (uint8_t)k;
         }
-        __syncthreads();
+        crowded = __syncthreads_or(shared_cell) != 0;
     }
 
     // Exact branch-free binary search; out of line on purpose (rare, keeps the hot loop small).
@@ -149,28 +146,16 @@ template <typename T, int B> struct Bucketizer<T, B, false> {
     }
 
     __device__ __forceinline__ void lookup(const float (&x)[8], uint32_t (&code)[8]) const {
-        uint32_t entry[8];
+        if (crowded) {  // block-uniform
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if constexpr (kByteEntries) {
-                entry[j] = lds_u8(entry_address(x[j]));
-            } else {
-                const uint32_t base = __float_as_uint(lut_base);
-                entry[j] = lds_u16(base + 2 * (entry_address(x[j]) - base));
-            }
+            for (int j = 0; j < 8; ++j) code[j] = exact(table, x[j]);
+            return;
         }
-        const uint32_t any = (entry[0] | entry[1] | entry[2]) | (entry[3] | entry[4] | entry[5]) |
-                             (entry[6] | entry[7]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t slot = kByteEntries ? entry[j] : (entry[j] & 0xffu);
-            code[j] = entry[j] + (lds_f32(table_base + 4 * slot) < x[j] ? 1u : 0u);
-        }
-        if (any & kCrowded) {  // some cell holds several bounds: resolve those exactly
+        for (int j = 0; j < 8; ++j) code[j] = lds_u8(entry_address(x[j]));
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (entry[j] & kCrowded) code[j] = exact(table, x[j]);
-        }
+        for (int j = 0; j < 8; ++j)
+            if (lds_f32(table_base + 4 * code[j]) < x[j]) code[j] += 1;
     }
 };
 
@@ -201,12 +186,12 @@ struct SeluFn : EluFamily {  // codec.cu:588-600
                     1.0f} {}
 };
 // GELU.  ATen evaluates  (0.5 x) * (1 + erf(x / sqrt 2))  with libdevice erff, a two-branch
-// routine that costs ~9 ALU-pipe selects per element.  Here erf comes from one branch-free
-// evaluation of erfc:   erfc(t) = s * 2^(P(s) - log2(e) t^2),  s = 1 / (1 + t/2),  t = |x|/sqrt 2
-// (P fitted by tools/fit_gelu.py; degree 9 keeps erf within one fp32 ulp-of-one, degree 5 is
-// enough for a bf16 result), then  erf = copysign(1 - erfc, x)  and ATen's last two steps
-// verbatim, so rounding and the 1+erf cancellation in the negative tail behave like F.gelu.
-// 12 FMA-pipe ops + 2 MUFU + 1 ALU op instead of ~33 instructions.
+// routine that costs ~9 ALU-pipe selects per element -- affordable in fp32, where the kernel is
+// close to the HBM bound anyway, but not in bf16 (half the bytes per element).  For bf16 erf
+// comes from one branch-free evaluation of erfc:
+//     erfc(t) = s * 2^(P(s) - log2(e) t^2),   s = 1 / (1 + t/2),   t = |x| / sqrt 2
+// with a degree-5 P fitted by tools/fit_gelu.py (0.1 % of results differ from the fp32-exact
+// bf16 rounding, by one bf16 ulp): 11 FMA-pipe ops + 2 MUFU, no ALU-pipe op.
 __device__ __forceinline__ float rcp_approx(float v) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
@@ -220,31 +205,27 @@ __device__ __forceinline__ float ex2_approx(float v) {
 struct GeluFn {  // codec.cu:539-544 (x * normcdf(x))
     __host__ GeluFn(double, double) {}
     template <typename T> __device__ __forceinline__ float eval(float x) const {
-        const float t = fabsf(x) * 0.70710678118654752440f;
-        const float s = rcp_approx(fmaf(t, 0.5f, 1.0f));
-        float p;
-        if constexpr (sizeof(T) == 2) {
-            p = 2.816799879e-01f;
-            p = fmaf(p, s, -8.819190860e-01f);
+        if constexpr (sizeof(T) == 4) {
+            // fp32: ATen's expression with libdevice erff, bit for bit F.gelu.  (A more accurate
+            // erf lands on a different point of the 2^-24 grid of 1 + erf than erff does in the
+            // negative tail, and the reference's own test -- L2 distance to F.gelu below 1e-6
+            // on linspace(-5, 5, 101) -- then fails at 1.1e-6; see DESIGN.md.)
+            return (x * 0.5f) * (1.0f + erff(x * 0.70710678118654752440f));
+        } else {
+            // bf16: the result is rounded to 8 bits, so erfc may come from the short branch-free
+            // evaluation above.  s = 1 / (1 + t/2) with t = |x| / sqrt 2.
+            const float s = rcp_approx(fmaf(fabsf(x), 0.35355339059327376220f, 1.0f));
+            float p = fmaf(2.816799879e-01f, s, -8.819190860e-01f);
             p = fmaf(p, s, 5.309718251e-01f);
             p = fmaf(p, s, 4.433360100e-01f);
             p = fmaf(p, s, 1.451876998e+00f);
             p = fmaf(p, s, -1.825967312e+00f);
-        } else {
-            p = 2.534233928e-01f;
-            p = fmaf(p, s, -1.219192386e+00f);
-            p = fmaf(p, s, 2.214311123e+00f);
-            p = fmaf(p, s, -1.711810946e+00f);
-            p = fmaf(p, s, 4.512821436e-01f);
-            p = fmaf(p, s, -2.884398699e-01f);
-            p = fmaf(p, s, 1.443251818e-01f);
-            p = fmaf(p, s, 5.390827656e-01f);
-            p = fmaf(p, s, 1.442767620e+00f);
-            p = fmaf(p, s, -1.825749040e+00f);
+            // erfc(t) = s * 2^(P(s) - log2(e) t^2),  log2(e) t^2 = (log2(e)/2) x^2
+            const float erfc_t = s * ex2_approx(fmaf(x * -0.72134752044448170368f, x, p));
+            // (x/2)(1 + erf(x/sqrt 2)) with erf = sign(x)(1 - erfc):  x/2 + |x/2| (1 - erfc)
+            const float half = x * 0.5f;
+            return fmaf(fabsf(half), 1.0f - erfc_t, half);
         }
-        const float erfc_t = s * ex2_approx(fmaf(t * -1.4426950408889634f, t, p));
-        const float erf_x = copysignf(1.0f - erfc_t, x);
-        return (x * 0.5f) * (1.0f + erf_x);
     }
 };
 struct HardswishFn {  // codec.cu:546-564
@@ -299,6 +280,7 @@ struct TanhshrinkFn {  // codec.cu:648-653
 // Forward op of a continuous activation: y = fn(x), code = bucket(x), eight values at a time.
 template <class Fn, typename T, int B> struct QuantizeOp {
     static constexpr int kBits = B;
+    static constexpr bool kHeavy = true;  // transcendental math: see TileConfig in launch.cuh
     using Scratch = typename Bucketizer<T, B>::Scratch;
     Fn fn;
     Bucketizer<T, B> bucket;
@@ -314,6 +296,7 @@ template <class Fn, typename T, int B> struct QuantizeOp {
 // (StepwiseBackwardKernel, fewbit/cuda/codec.cu:655-670).
 template <typename T, int B> struct LevelsOp {
     static constexpr int kBits = B;
+    static constexpr bool kHeavy = false;
     struct Scratch {
         float levels[1 << B];
     };
@@ -407,6 +390,7 @@ struct ThresholdFn {  // codec.cu:470-484
 
 template <class Fn> struct MaskOp {
     static constexpr int kBits = 1;
+    static constexpr bool kHeavy = false;
     using Scratch = NoScratch;
     Fn fn;
     __device__ __forceinline__ void prepare(Scratch &) {}
@@ -420,6 +404,7 @@ template <class Fn> struct MaskOp {
 // hardsigmoid :333-345: 1/6 | 0; leaky_relu :391-402: slope | 1).
 struct MaskFactorOp {
     static constexpr int kBits = 1;
+    static constexpr bool kHeavy = false;
     using Scratch = NoScratch;
     float on, off;
     __device__ __forceinline__ void prepare(Scratch &) {}

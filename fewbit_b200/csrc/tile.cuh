@@ -26,19 +26,39 @@ constexpr int kSubtile = 256;  // elements per warp per round of 128-bit loads
 
 // ---------------------------------------------------------------- global memory I/O ----
 
+// Tuning knobs (benchmarks/sweep.py builds variants with -D...): cache policy of the streaming
+// loads / stores (measured on B200: no effect, profiles/r01_tuning_sweep.md).
+#ifndef FEWBIT_LD_MODE
+#define FEWBIT_LD_MODE 1  // 0: ld.global   1: ld.global.L1::no_allocate   2: ld.global.cs
+#endif
+#ifndef FEWBIT_ST_MODE
+#define FEWBIT_ST_MODE 1  // 0: st.global   1: st.global.L1::no_allocate   2: st.global.cs
+#endif
+
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
     uint4 r;
     // Plain (coherent) load: x and y may alias, so the read-only .nc path is off limits.
-    // Streamed once -> do not keep the line in L1.
+#if FEWBIT_LD_MODE == 0
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+#elif FEWBIT_LD_MODE == 1
     asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+#else
+    asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];"
+#endif
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
 }
 
 __device__ __forceinline__ void stg_stream(uint4 *p, const uint4 &v) {
-    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
-                 "r"(v.y), "r"(v.z), "r"(v.w)
+#if FEWBIT_ST_MODE == 0
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};"
+#elif FEWBIT_ST_MODE == 1
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+#else
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};"
+#endif
+                 ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
 }
 
@@ -206,76 +226,99 @@ template <int B, int U> struct StripStorage {
     alignas(16) uint8_t bytes[kWarps][kBytes];
 };
 
-template <class Op, typename T, int U>
-__global__ void __launch_bounds__(kThreads) forward_tiles_kernel(const T *x, T *y, uint8_t *state,
-                                                                int64_t ntiles, Op op) {
+// One warp, `N` consecutive subtiles starting at subtile index `sub`.
+template <class Op, typename T, int N>
+__device__ __forceinline__ void forward_chunk(const Op &op, const T *x, T *y, uint8_t *state,
+                                              uint8_t *strip, int64_t sub, int lane) {
     constexpr int B = Op::kBits;
-    constexpr int kStrip = U * subtile_bytes<B>();
-    __shared__ StripStorage<B, U> strips;
-    __shared__ typename Op::Scratch scratch;
-    op.prepare(scratch);
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t *strip = strips.bytes[warp];
-    const int64_t stride = (int64_t)gridDim.x * kWarps;
-
-    for (int64_t tile = (int64_t)blockIdx.x * kWarps + warp; tile < ntiles; tile += stride) {
-        const T *xt = x + tile * (int64_t)(U * kSubtile);
-        T *yt = y + tile * (int64_t)(U * kSubtile);
-        float v[U][8];
+    constexpr int kBytes = N * subtile_bytes<B>();
+    const T *xt = x + sub * kSubtile;
+    T *yt = y + sub * kSubtile;
+    float v[N][8];
 #pragma unroll
-        for (int u = 0; u < U; ++u) Subtile<T>::load(xt + u * kSubtile, lane, v[u]);
+    for (int u = 0; u < N; ++u) Subtile<T>::load(xt + u * kSubtile, lane, v[u]);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            uint32_t code[8];
-            op.apply(v[u], code);
-            Subtile<T>::store(yt + u * kSubtile, lane, v[u]);
-            stage_codes<T, B>(strip + u * subtile_bytes<B>(), lane, code);
-        }
-        __syncwarp();
-        uint4 *out = reinterpret_cast<uint4 *>(state + tile * (int64_t)kStrip);
-        const uint4 *src = reinterpret_cast<const uint4 *>(strip);
-#pragma unroll
-        for (int i = lane; i < kStrip / 16; i += 32) stg_stream(out + i, src[i]);
-        __syncwarp();
+    for (int u = 0; u < N; ++u) {
+        uint32_t code[8];
+        op.apply(v[u], code);
+        Subtile<T>::store(yt + u * kSubtile, lane, v[u]);
+        stage_codes<T, B>(strip + u * subtile_bytes<B>(), lane, code);
     }
+    __syncwarp();
+    uint4 *out = reinterpret_cast<uint4 *>(state + sub * (int64_t)subtile_bytes<B>());
+    const uint4 *src = reinterpret_cast<const uint4 *>(strip);
+#pragma unroll
+    for (int i = lane; i < kBytes / 16; i += 32) stg_stream(out + i, src[i]);
+    __syncwarp();
 }
 
-template <class Op, typename T, int U>
-__global__ void __launch_bounds__(kThreads) backward_tiles_kernel(const uint8_t *state, const T *gout,
-                                                                 T *gin, int64_t ntiles, Op op) {
+template <class Op, typename T, int N>
+__device__ __forceinline__ void backward_chunk(const Op &op, const uint8_t *state, const T *gout,
+                                               T *gin, uint8_t *strip, int64_t sub, int lane) {
     constexpr int B = Op::kBits;
-    constexpr int kStrip = U * subtile_bytes<B>();
+    constexpr int kBytes = N * subtile_bytes<B>();
+    const T *gt = gout + sub * kSubtile;
+    T *dt = gin + sub * kSubtile;
+    const uint4 *packed = reinterpret_cast<const uint4 *>(state + sub * (int64_t)subtile_bytes<B>());
+    uint4 *dst = reinterpret_cast<uint4 *>(strip);
+    float v[N][8];
+#pragma unroll
+    for (int u = 0; u < N; ++u) Subtile<T>::load(gt + u * kSubtile, lane, v[u]);
+#pragma unroll
+    for (int i = lane; i < kBytes / 16; i += 32) dst[i] = ldg_stream(packed + i);
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        uint32_t code[8];
+        fetch_codes<T, B>(reinterpret_cast<const uint32_t *>(strip + u * subtile_bytes<B>()), lane,
+                          code);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[u][j] = op.factor(code[j]) * v[u][j];
+        Subtile<T>::store(dt + u * kSubtile, lane, v[u]);
+    }
+    __syncwarp();
+}
+
+// Work split of the persistent grid: every warp takes the same number of full warp tiles
+// (strided, so that the grid sweeps memory as one window); what is left over (< one tile per
+// warp) is handed out in single subtiles, which bounds the imbalance at 256 elements per warp
+// instead of U * 256.
+template <class Op, typename T, int U, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) forward_tiles_kernel(const T *x, T *y, uint8_t *state,
+                                                                int64_t ntiles, Op op) {
+    constexpr int B = Op::kBits;
     __shared__ StripStorage<B, U> strips;
     __shared__ typename Op::Scratch scratch;
     op.prepare(scratch);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *strip = strips.bytes[warp];
-    const int64_t stride = (int64_t)gridDim.x * kWarps;
+    const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+    const int64_t me = (int64_t)blockIdx.x * kWarps + warp;
+    const int64_t even = ntiles / nwarps * nwarps;
+    for (int64_t tile = me; tile < even; tile += nwarps)
+        forward_chunk<Op, T, U>(op, x, y, state, strip, tile * U, lane);
+    for (int64_t sub = even * U + me; sub < ntiles * U; sub += nwarps)
+        forward_chunk<Op, T, 1>(op, x, y, state, strip, sub, lane);
+}
 
-    for (int64_t tile = (int64_t)blockIdx.x * kWarps + warp; tile < ntiles; tile += stride) {
-        const T *gt = gout + tile * (int64_t)(U * kSubtile);
-        T *dt = gin + tile * (int64_t)(U * kSubtile);
-        const uint4 *packed = reinterpret_cast<const uint4 *>(state + tile * (int64_t)kStrip);
-        uint4 *dst = reinterpret_cast<uint4 *>(strip);
-        float v[U][8];
-#pragma unroll
-        for (int u = 0; u < U; ++u) Subtile<T>::load(gt + u * kSubtile, lane, v[u]);
-#pragma unroll
-        for (int i = lane; i < kStrip / 16; i += 32) dst[i] = ldg_stream(packed + i);
-        __syncwarp();
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            uint32_t code[8];
-            fetch_codes<T, B>(reinterpret_cast<const uint32_t *>(strip + u * subtile_bytes<B>()),
-                              lane, code);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[u][j] = op.factor(code[j]) * v[u][j];
-            Subtile<T>::store(dt + u * kSubtile, lane, v[u]);
-        }
-        __syncwarp();
-    }
+template <class Op, typename T, int U, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) backward_tiles_kernel(const uint8_t *state, const T *gout,
+                                                                 T *gin, int64_t ntiles, Op op) {
+    constexpr int B = Op::kBits;
+    __shared__ StripStorage<B, U> strips;
+    __shared__ typename Op::Scratch scratch;
+    op.prepare(scratch);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *strip = strips.bytes[warp];
+    const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+    const int64_t me = (int64_t)blockIdx.x * kWarps + warp;
+    const int64_t even = ntiles / nwarps * nwarps;
+    for (int64_t tile = me; tile < even; tile += nwarps)
+        backward_chunk<Op, T, U>(op, state, gout, gin, strip, tile * U, lane);
+    for (int64_t sub = even * U + me; sub < ntiles * U; sub += nwarps)
+        backward_chunk<Op, T, 1>(op, state, gout, gin, strip, sub, lane);
 }
 
 // Ragged / unaligned path: one thread per octet, guarded scalar accesses.  Used for the

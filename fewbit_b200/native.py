@@ -11,7 +11,10 @@ from pathlib import Path
 
 import torch
 
-LIBRARY = Path(__file__).with_name('libfewbit_b200.so')
+import os
+
+# FEWBIT_B200_LIBRARY: load another build of the kernels (tuning sweeps only).
+LIBRARY = Path(os.environ.get('FEWBIT_B200_LIBRARY') or Path(__file__).with_name('libfewbit_b200.so'))
 
 F32, BF16 = 0, 1
 CONTINUOUS = ('celu', 'elu', 'gelu', 'hardswish', 'logsigmoid', 'mish', 'selu', 'sigmoid', 'silu',

@@ -11,6 +11,12 @@ namespace ``fewbit`` -- the very namespace the product library registers.
                                    (fewbit/cpu/gelu.cc:7-31, 33-45)
     python oracle/ref_runner.py bench --n N --bits B --repeats R [--threads T]
         prints one JSON line with the median seconds of quantize and quantize_backward.
+    python oracle/ref_runner.py cuda in.npz out.npz          (needs a GPU)
+        runs the reference's CUDA operators (oracle/_ref/libfewbit_ref_cuda.so = unmodified
+        fewbit/cuda/codec.cu + activation.cc built for sm_100) on every case of in.npz and
+        stores y, the codes its kernel chose and its gradient.
+    python oracle/ref_runner.py cuda-bench                   (needs a GPU)
+        times the reference CUDA kernels on the benchmark shapes (fp32 only: it has no bf16).
 """
 from __future__ import annotations
 
@@ -25,6 +31,7 @@ import torch
 
 HERE = Path(__file__).resolve().parent
 LIB = HERE / '_ref' / 'libfewbit_ref.so'
+LIB_CUDA = HERE / '_ref' / 'libfewbit_ref_cuda.so'
 
 
 def load():
@@ -93,6 +100,104 @@ def cmd_bench(args):
                       'fwd_s': float(np.median(tf)), 'bwd_s': float(np.median(tb))}))
 
 
+def load_cuda():
+    if not LIB_CUDA.exists():
+        raise SystemExit(f'{LIB_CUDA} is missing: run `make -C oracle ref` where /root/reference exists')
+    torch.ops.load_library(str(LIB_CUDA))
+
+
+def padded_view(bounds: torch.Tensor, bits: int) -> torch.Tensor:
+    """The reference searches 2^(bits+1) - 1 entries (nobits = bits + 1) and so
+    reads past the bounds it is given; it only works on a *view* followed by large sentinels
+    (as borders[1:-1] of the store is).  Give it exactly that."""
+    pad = torch.full((2 << bits, ), float('inf'), device=bounds.device, dtype=bounds.dtype)
+    return torch.cat([bounds, pad])[:bounds.numel()]
+
+
+def cmd_cuda(args):
+    load_cuda()
+    dev = torch.device('cuda:0')
+    out = {}
+    with np.load(args.inp, allow_pickle=False) as npz:
+        keys = sorted({k.split('/')[0] for k in npz.keys()})
+        for key in keys:
+            name = str(npz[f'{key}/name'])
+            params = [float(v) for v in npz[f'{key}/params']]
+            x = torch.from_numpy(npz[f'{key}/x']).to(dev)
+            g = torch.from_numpy(npz[f'{key}/g']).to(dev)
+            assert x.numel() % 1024 == 0, 'reference writes out of bounds on ragged sizes (App. C-7)'
+            op = getattr(torch.ops.fewbit, name)
+            if f'{key}/bounds' in npz:
+                bounds = torch.from_numpy(npz[f'{key}/bounds']).to(dev)
+                levels = torch.from_numpy(npz[f'{key}/levels']).to(dev)
+                bits = max(1, int(np.ceil(np.log2(levels.numel()))))
+                view = padded_view(bounds, bits)
+                leaf = x.clone().requires_grad_()
+                y = op(leaf * 1.0, view, levels, *params)
+                y.backward(g)
+                # codes: levels = 0, 1, 2, ... and g = 1 make the gradient equal to the code
+                probe = x.clone().requires_grad_()
+                ramp = torch.arange(levels.numel(), device=dev, dtype=torch.float32)
+                op(probe * 1.0, view, ramp, *params).backward(torch.ones_like(x))
+                out[f'{key}/codes'] = probe.grad.cpu().numpy().astype(np.int32)
+            else:
+                leaf = x.clone().requires_grad_()
+                y = op(leaf * 1.0, *params)
+                y.backward(g)
+            out[f'{key}/y'] = y.detach().cpu().numpy()
+            out[f'{key}/gin'] = leaf.grad.cpu().numpy()
+    torch.cuda.synchronize()
+    np.savez(args.out, **out)
+
+
+def cmd_cuda_bench(args):
+    load_cuda()
+    dev = torch.device('cuda:0')
+    torch.manual_seed(0)
+    res = {}
+
+    def timed(fn, reps=10, rounds=5):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(rounds):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record(torch.cuda.default_stream())
+            for _ in range(reps):
+                fn()
+            b.record(torch.cuda.default_stream())   # the reference launches on the legacy stream
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) / reps)
+        return float(np.median(ts))
+
+    from statistics import NormalDist  # noqa: F401
+    n = 128 * 128 * 3072
+    bounds = torch.tensor([-2.41658115, -0.710008025, -0.325840563, 1.06942185e-04, 0.326057166,
+                           0.710240841, 2.41447878], device=dev)
+    levels = torch.tensor([-1.9399123e-04, -8.8279128e-02, 0.12568383, 0.37231442, 0.62785137,
+                           0.87445050, 1.0883480, 1.0001949], device=dev)
+    view = padded_view(bounds, 3)
+    x = torch.randn(n, device=dev) * 2
+    g = torch.randn(n, device=dev)
+    with torch.no_grad():
+        ms = timed(lambda: torch.ops.fewbit.gelu(x, view, levels))
+    # the reference packs bits+1 = 4 bits per element: count the bytes it really moves
+    res['gelu3_f32_fwd'] = {'ms': ms, 'GBps_algorithmic_3bit': n * (8 + 3 / 8) / ms / 1e6,
+                            'GBps_own_4bit': n * (8 + 4 / 8) / ms / 1e6}
+    leaf = x.clone().requires_grad_()
+    y = torch.ops.fewbit.gelu(leaf * 1.0, view, levels)
+    ms = timed(lambda: torch.autograd.grad(y, leaf, g, retain_graph=True))
+    res['gelu3_f32_bwd'] = {'ms': ms, 'GBps_algorithmic_3bit': n * (8 + 3 / 8) / ms / 1e6,
+                            'note': 'autograd.grad: kernel + empty_like + mul by 1.0 upstream'}
+    n = 1 << 28                                  # 1 GiB of fp32 (the reference has no bf16 path)
+    x = torch.randn(n, device=dev) * 2
+    with torch.no_grad():
+        ms = timed(lambda: torch.ops.fewbit.relu(x))
+    res['relu_f32_1GiB_fwd'] = {'ms': ms, 'GBps_algorithmic': n * (8 + 1 / 8) / ms / 1e6}
+    print(json.dumps(res))
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser()
     sub = ap.add_subparsers(dest='cmd', required=True)
@@ -107,6 +212,12 @@ def main(argv=None):
     b.add_argument('--threads', type=int, default=0)
     b.add_argument('--dtype', default='f32')
     b.set_defaults(fn=cmd_bench)
+    c = sub.add_parser('cuda')
+    c.add_argument('inp')
+    c.add_argument('out')
+    c.set_defaults(fn=cmd_cuda)
+    cb = sub.add_parser('cuda-bench')
+    cb.set_defaults(fn=cmd_cuda_bench)
     args = ap.parse_args(argv)
     args.fn(args)
 

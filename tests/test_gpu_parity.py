@@ -178,6 +178,35 @@ def test_nan_maps_to_code_zero_and_short_tables():
 
 
 @pytest.mark.parametrize('tag', DTYPES)
+@pytest.mark.parametrize('bits', [3, 4, 6, 8])
+def test_crowded_and_degenerate_tables(bits, tag):
+    """Tables the cell look-up cannot separate (clustered / duplicated / single borders) must
+    take the exact search and still produce lower_bound codes."""
+    dtype = DTYPES[tag]
+    nb = (1 << bits) - 1
+    gen = torch.Generator().manual_seed(bits)
+    tables = {
+        'clustered': torch.cat([torch.tensor([-3.0]), torch.linspace(0.5, 0.5001, nb - 2), torch.tensor([4.0])]),
+        'duplicates': torch.sort(torch.randint(-3, 4, (nb, ), generator=gen).float()).values,
+        'all_equal': torch.full((nb, ), 0.25),
+        'single': torch.tensor([0.1]),
+        'short': torch.sort(torch.randn(nb // 2 + 1, generator=gen)).values,
+    }
+    for label, bounds in tables.items():
+        bounds = bounds.to(dtype).to(DEV)
+        levels = torch.linspace(-1, 1, bounds.numel() + 1).to(dtype).to(DEV)
+        x, g = inputs(4099, bounds, dtype, seed=bits)
+        x[100:100 + min(bounds.numel(), 64)] = bounds[:64]
+        y, gin = torch.empty_like(x), torch.empty_like(g)
+        state = native.new_state(x, bits)
+        native.stepwise_forward('sigmoid', x, y, state, bits, bounds)
+        native.stepwise_backward(state, g, gin, bits, levels)
+        y_ref, state_ref = oracle.stepwise_forward('sigmoid', to_np(x), to_np(bounds), bits)
+        assert np.array_equal(state.cpu().numpy(), state_ref), f'{label}/{tag}/bits={bits}'
+        assert np.array_equal(to_np(gin), oracle.stepwise_backward(state_ref, to_np(g), to_np(levels), bits))
+
+
+@pytest.mark.parametrize('tag', DTYPES)
 def test_in_place_unaligned_and_empty(tag):
     dtype = DTYPES[tag]
     bounds, levels = table('silu', 3, dtype)
