@@ -66,6 +66,21 @@ def _sketch_matrix(kind: str, rows: int, cols: int, generator: T.Generator, devi
     raise ValueError(f'Unexpected matmul type: {kind}.')
 
 
+def _linear_owning_output(input_view: T.Tensor, weight: T.Tensor, bias: Optional[T.Tensor],
+                          shape) -> T.Tensor:
+    """``F.linear`` whose result owns its storage.  For inputs with more than two dimensions
+    ``F.linear`` returns a view of a 2-D product; a view created inside a custom Function may
+    not be modified in place afterwards, which is exactly what the in-place few-bit
+    activations do to the output of the preceding linear layer."""
+    out = input_view.new_empty(*shape[:-1], weight.shape[0])
+    flat = out.view(-1, weight.shape[0])
+    if bias is not None:
+        T.addmm(bias, input_view, weight.t(), out=flat)
+    else:
+        T.mm(input_view, weight.t(), out=flat)
+    return out
+
+
 class LinearGRPFunc(T.autograd.Function):
 
     @staticmethod
@@ -101,7 +116,7 @@ class LinearGRPFunc(T.autograd.Function):
         ctx.matmul = matmul
         ctx.generator_state = generator_state
         ctx.generator_device = generator.device
-        return F.linear(input, weight, bias)
+        return _linear_owning_output(input_view, weight, bias, input.shape)
 
     @staticmethod
     def backward(ctx, grad_output):

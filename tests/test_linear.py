@@ -104,3 +104,16 @@ def test_user_generator_is_honoured_and_replayed():
     layer.zero_grad()
     layer(x).sum().backward()                        # generator advanced: a different sketch
     assert not torch.equal(layer.weight.grad, grads[0])
+
+
+def test_output_can_be_modified_in_place():
+    """3-bit GELU (in place) directly after a RandomizedLinear on a 3-D input: the linear's
+    output must own its storage (regression: 'view ... modified inplace' from autograd)."""
+    layer = fewbit.LinearGRP(16, 32, proj_dim_ratio=0.5)
+    x = torch.randn(4, 8, 16, requires_grad=True)
+    y = layer(x)
+    assert not y._is_view() and y.shape == (4, 8, 32)
+    torch.testing.assert_close(y, torch.nn.functional.linear(x, layer.weight, layer.bias))
+    z = y.relu_()                      # any in-place op on the output
+    z.sum().backward()
+    assert layer.weight.grad is not None and x.grad is not None
