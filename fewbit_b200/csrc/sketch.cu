@@ -1,0 +1,464 @@
+// fewbit_b200 -- RandomizedLinear's projection  out = scale * S X  on tcgen05 tensor cores.
+//
+//   X   : [N tokens, D features] bf16, row-major (TMA source; never copied or transposed)
+//   S   : [P, N] random sketch, N(0,1) or +-1/2 entries, NEVER materialised: every element is
+//         a pure function of (seed, offset, p, n) -- Philox4x32-10 keyed by the seed, counter
+//         (n / 4, p, offset) -> four entries -- so forward and backward regenerate the same S.
+//   out : [P, D] fp32
+// Replaces `proj = randn(P, N); proj_input = (proj @ input_view) / P` and `proj @ grad_output`
+// of the reference (fewbit/functional/linear.py:133-137, 196-199), which writes S (214 MB at
+// RoBERTa shapes) to HBM twice per layer and multiplies in fp32 on the CUDA cores.
+//
+// Mapping onto the MMA.  The contraction runs over tokens, so with X as it lies in memory the
+// feature axis is the contiguous one: X^T is an "MN-major" operand.  We therefore compute
+// out^T tiles:  D[d, p] += A[d, n] * B[p, n]   with
+//   A = X^T  : M = 128 features per MMA, MN-major, 128B swizzle, loaded by TMA as 64-token x
+//              64-feature boxes (8 KB each, exactly the canonical MN-major SW128 atom stack);
+//   B = S    : N = BN sketch rows (<= 160, multiple of 16), K-major, 128B swizzle, written to
+//              shared memory by the generator warps;
+//   D        : fp32 in TMEM, 128 lanes (features) x BN columns per 128-feature block; a CTA owns
+//              up to 3 blocks (384 features -> 480 of the 512 TMEM columns), so one generated S
+//              tile feeds three MMAs and X is re-read from L2 only P/BN times.
+// The TMEM lane = feature orientation also makes the epilogue store coalesced: for a fixed
+// sketch row the 32 lanes of a warp hold 32 consecutive features.
+//
+// CTA = 8 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-7 generate
+// S; warps 4-7 then run the epilogue (tcgen05.ld -> scale -> global).  Three-stage mbarrier
+// pipeline: full_x (TMA bytes), full_s (generator warps), empty (tcgen05.commit).
+// Grid = (ceil(P / BN), ceil(D / 384), split_k); split-K partials are reduced by a tiny kernel.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+
+#include "../../include/fewbit_b200.h"
+
+namespace fewbit {
+
+void note_launch();
+int sm_count();
+
+namespace sketch {
+
+constexpr int kThreads = 256;
+constexpr int kStages = 3;
+constexpr int kBlockK = 64;            // tokens per stage
+constexpr int kFeaturesPerCta = 384;   // 3 MMA M-blocks of 128
+constexpr int kMaxRows = 160;          // BN: sketch rows per CTA (TMEM: 3 * 160 <= 512 columns)
+constexpr int kBoxBytes = 64 * 64 * 2;                        // one TMA box: 64 tokens x 64 features
+constexpr int kXStageBytes = (kFeaturesPerCta / 64) * kBoxBytes;   // 49152
+constexpr int kSStageBytes = kMaxRows * 128;                  // 20480: BN rows x 64 bf16
+constexpr int kStageBytes = kXStageBytes + kSStageBytes;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* alignment */ + 256 /* barriers */;
+constexpr int kGeneratorWarps = 6;
+constexpr int kTmemColumns = 512;
+
+// ---------------------------------------------------------------------------- PTX ----
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_load16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+          "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100): start address, leading
+// and stride byte offsets in 16-byte units, version 1, layout SWIZZLE_128B = 2.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+           ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ------------------------------------------------------------------------- random ----
+
+struct Philox {
+    uint32_t k0, k1;
+    __device__ __forceinline__ uint4 operator()(uint4 c) const {
+        uint32_t a = k0, b = k1;
+#pragma unroll
+        for (int round = 0; round < 10; ++round) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+            c = make_uint4(hi1 ^ c.y ^ a, lo1, hi0 ^ c.w ^ b, lo0);
+            a += 0x9E3779B9u;
+            b += 0xBB67AE85u;
+        }
+        return c;
+    }
+};
+
+__device__ __forceinline__ float unit_open(uint32_t bits) {  // (0, 1), 23 random bits
+    return __uint_as_float(0x3f800000u | (bits >> 9)) - (1.0f - 5.9604645e-8f);
+}
+
+// Entries S[p][4q .. 4q+3] as two packed bf16x2 words.  kind 0: N(0,1) by Box-Muller on the
+// four Philox words; kind 1: +-1/2 from their top bits.
+__device__ __forceinline__ uint2 sketch_quad(const Philox &rng, uint32_t q, uint32_t p, uint32_t off_lo,
+                                             uint32_t off_hi, int kind) {
+    const uint4 r = rng(make_uint4(q, p, off_lo, off_hi));
+    float z0, z1, z2, z3;
+    if (kind == 0) {
+        const float r0 = sqrtf(-1.3862943611198906f * __log2f(unit_open(r.x)));   // sqrt(-2 ln u)
+        const float r1 = sqrtf(-1.3862943611198906f * __log2f(unit_open(r.z)));
+        float s0, c0, s1, c1;
+        __sincosf(6.283185307179586f * unit_open(r.y), &s0, &c0);
+        __sincosf(6.283185307179586f * unit_open(r.w), &s1, &c1);
+        z0 = r0 * c0, z1 = r0 * s0, z2 = r1 * c1, z3 = r1 * s1;
+    } else {
+        z0 = (r.x >> 31) ? 0.5f : -0.5f, z1 = (r.y >> 31) ? 0.5f : -0.5f;
+        z2 = (r.z >> 31) ? 0.5f : -0.5f, z3 = (r.w >> 31) ? 0.5f : -0.5f;
+    }
+    uint2 out;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(out.x) : "f"(z1), "f"(z0));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(out.y) : "f"(z3), "f"(z2));
+    return out;
+}
+
+// --------------------------------------------------------------------------- kernel ----
+
+struct Params {
+    float *out;          // [P, D] (split_k == 1) or partials [split_k, P, D]
+    int64_t tokens;      // N
+    int features;        // D
+    int rows;            // P
+    int block_rows;      // BN
+    int kblocks_per_split;
+    int split_k;
+    float scale;         // applied here only when split_k == 1
+    uint32_t seed_lo, seed_hi, off_lo, off_hi;
+    int kind;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
+    extern __shared__ uint8_t smem_raw[];
+    // 128B-swizzled tiles need 1024-byte alignment.
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * kStages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p0 = blockIdx.x * prm.block_rows;
+    const int d0 = blockIdx.y * kFeaturesPerCta;
+    const int bn = prm.block_rows;
+    const int nblocks = min(3, (prm.features - d0 + 127) / 128);   // 128-feature MMA blocks
+    const int nboxes = min(6, (prm.features - d0 + 63) / 64);
+    const int64_t total_kb = (prm.tokens + kBlockK - 1) / kBlockK;
+    const int64_t kb_begin = (int64_t)blockIdx.z * prm.kblocks_per_split;
+    const int64_t kb_end = min(total_kb, kb_begin + prm.kblocks_per_split);
+    const int iters = (int)max((int64_t)0, kb_end - kb_begin);
+
+    auto full_x = [&](int s) { return smem_addr(bars + s); };
+    auto full_s = [&](int s) { return smem_addr(bars + kStages + s); };
+    auto empty = [&](int s) { return smem_addr(bars + 2 * kStages + s); };
+    const uint32_t accum_full = smem_addr(bars + 3 * kStages);
+    auto x_stage = [&](int s) { return smem_addr(smem + s * kStageBytes); };
+    auto s_stage = [&](int s) { return smem_addr(smem + s * kStageBytes + kXStageBytes); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_x(s), 1);
+            mbar_init(full_s(s), kGeneratorWarps);
+            mbar_init(empty(s), 1);
+        }
+        mbar_init(accum_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM allocation is warp-wide; the same warp frees it
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_addr(tmem_slot)),
+                     "r"(kTmemColumns));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer ----
+        if (lane == 0) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % kStages;
+                mbar_wait(empty(s), ((it / kStages) & 1) ^ 1);
+                mbar_expect_tx(full_x(s), nboxes * kBoxBytes);
+                const int token = (int)((kb_begin + it) * kBlockK);
+                for (int b = 0; b < nboxes; ++b)
+                    tma_load_2d(x_stage(s) + b * kBoxBytes, &x_map, d0 + 64 * b, token, full_x(s));
+            }
+        }
+    } else if (warp == 1) {
+        // -------------------------------------------------------------- MMA issuer ----
+        if (lane == 0) {
+            // cute::UMMA::InstrDescriptor: D = f32, A = B = bf16, A MN-major, B K-major, N, M = 128.
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (0u << 16) |
+                                   ((uint32_t)(bn >> 3) << 17) | ((128u >> 4) << 24);
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % kStages;
+                const uint32_t parity = (it / kStages) & 1;
+                mbar_wait(full_x(s), parity);
+                mbar_wait(full_s(s), parity);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    // B: rows of 128 B (64 tokens), 8-row groups 1024 B apart; +32 B per 16 tokens.
+                    const uint64_t desc_b = smem_desc(s_stage(s) + 32 * k, 16, 1024);
+                    for (int m = 0; m < nblocks; ++m) {
+                        // A: 64-feature groups 8192 B apart (LBO), 8-token groups 1024 B apart
+                        // (SBO); +2048 B per 16 tokens; 128 features = two boxes.
+                        const uint64_t desc_a = smem_desc(x_stage(s) + m * 2 * kBoxBytes + 2048 * k, kBoxBytes, 1024);
+                        umma_bf16(tmem_base + m * kMaxRows, desc_a, desc_b, idesc, (it | k) != 0);
+                    }
+                }
+                umma_commit(empty(s));        // smem slot reusable once these MMAs have read it
+            }
+            umma_commit(accum_full);          // accumulators complete
+        }
+    } else {
+        // -------------------------------------------------------------- generators ----
+        const Philox rng{prm.seed_lo, prm.seed_hi};
+        const int gt = threadIdx.x - 64;                       // 0 .. 191
+        const int quads = bn * (kBlockK / 4);                  // per stage: bn rows x 16 quads
+        for (int it = 0; it < iters; ++it) {
+            const int s = it % kStages;
+            mbar_wait(empty(s), ((it / kStages) & 1) ^ 1);
+            uint8_t *tile = smem + s * kStageBytes + kXStageBytes;
+            const uint32_t q0 = (uint32_t)((kb_begin + it) * (kBlockK / 4));
+            for (int i = gt; i < quads; i += kGeneratorWarps * 32) {
+                const int row = i >> 4, q = i & 15;
+                const uint2 v = sketch_quad(rng, q0 + q, (uint32_t)(p0 + row), prm.off_lo, prm.off_hi, prm.kind);
+                // K-major SW128: 16-byte chunk index XOR (row mod 8)
+                const int chunk = (q >> 1) ^ (row & 7);
+                *reinterpret_cast<uint2 *>(tile + (row >> 3) * 1024 + (row & 7) * 128 + chunk * 16 + (q & 1) * 8) = v;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_s(s));
+        }
+        // ---------------------------------------------------------------- epilogue ----
+        if (warp >= 4) {
+            mbar_wait(accum_full, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int quarter = warp & 3;                       // TMEM lanes [32q, 32q + 32)
+            float *out = prm.out + (prm.split_k > 1 ? (int64_t)blockIdx.z * prm.rows * prm.features : 0);
+            const float scale = prm.split_k > 1 ? 1.0f : prm.scale;
+            for (int m = 0; m < nblocks; ++m) {
+                const int d = d0 + m * 128 + quarter * 32 + lane;
+                for (int c = 0; c < bn; c += 16) {
+                    uint32_t v[16];
+                    tmem_load16(tmem_base + ((uint32_t)(quarter * 32) << 16) + m * kMaxRows + c, v);
+                    if (iters == 0) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = 0;
+                    }
+                    if (d < prm.features) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int p = p0 + c + j;
+                            if (p < prm.rows) out[(int64_t)p * prm.features + d] = __uint_as_float(v[j]) * scale;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"(kTmemColumns));
+    }
+}
+
+__global__ void reduce_splits_kernel(const float *partials, float *out, int64_t count, int splits,
+                                     float scale) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float acc = 0.0f;
+        for (int s = 0; s < splits; ++s) acc += partials[(int64_t)s * count + i];
+        out[i] = acc * scale;
+    }
+}
+
+// S itself, for tests and diagnostics only (the product never materialises it).
+__global__ void sketch_matrix_kernel(__nv_bfloat16 *s, int rows, int64_t cols, Params prm) {
+    const Philox rng{prm.seed_lo, prm.seed_hi};
+    const int64_t quads_per_row = (cols + 3) / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * quads_per_row;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i / quads_per_row, q = i % quads_per_row;
+        const uint2 v = sketch_quad(rng, (uint32_t)q, (uint32_t)p, prm.off_lo, prm.off_hi, prm.kind);
+        const uint16_t e[4] = {(uint16_t)v.x, (uint16_t)(v.x >> 16), (uint16_t)v.y, (uint16_t)(v.y >> 16)};
+        for (int j = 0; j < 4; ++j)
+            if (4 * q + j < cols) reinterpret_cast<uint16_t *>(s)[p * cols + 4 * q + j] = e[j];
+    }
+}
+
+// ----------------------------------------------------------------------------- host ----
+
+using EncodeTiled = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                 CUtensorMapFloatOOBfill);
+
+static EncodeTiled encode_tiled() {
+    static EncodeTiled fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult status;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &status) == cudaSuccess &&
+            status == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiled>(ptr);
+    }
+    return fn;
+}
+
+// Pick BN (multiple of 16, <= 160) and split_k: minimise  waves * (time of one CTA), where a
+// CTA's main loop costs ~BN per 64-token block (S generation and MMA both scale with BN) plus a
+// fixed prologue/epilogue worth ~6 blocks at BN = 160.
+static void plan(int rows, int features, int64_t tokens, int sms, int &bn, int &split_k) {
+    const int dtiles = (features + kFeaturesPerCta - 1) / kFeaturesPerCta;
+    const int64_t kblocks = std::max<int64_t>(1, (tokens + kBlockK - 1) / kBlockK);
+    double best = 1e300;
+    bn = 160, split_k = 1;
+    for (int cand = 160; cand >= 64; cand -= 16) {
+        const int ptiles = (rows + cand - 1) / cand;
+        for (int sk = 1; sk <= 8 && sk <= kblocks; ++sk) {
+            const int64_t ctas = (int64_t)ptiles * dtiles * sk;
+            const int64_t waves = (ctas + sms - 1) / sms;
+            const double per_cta = (double)((kblocks + sk - 1) / sk) * cand + 6.0 * 160.0;
+            const double cost = (double)waves * per_cta * (1.0 + 0.01 * (sk - 1));
+            if (cost < best) best = cost, bn = cand, split_k = sk;
+        }
+    }
+}
+
+}  // namespace sketch
+}  // namespace fewbit
+
+using namespace fewbit;
+using namespace fewbit::sketch;
+
+extern "C" {
+
+size_t fewbit_sketch_workspace_bytes(int64_t tokens, int features, int rows) {
+    int bn, split_k;
+    plan(rows, features, tokens, sm_count(), bn, split_k);
+    return split_k > 1 ? (size_t)split_k * rows * features * sizeof(float) : 0;
+}
+
+int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t tokens, int features,
+                          int rows, int kind, float scale, uint64_t seed, uint64_t offset, void *stream) {
+    if (tokens < 0 || features <= 0 || rows <= 0 || (kind != 0 && kind != 1)) return FEWBIT_EINVAL;
+    if (!x || !out) return FEWBIT_EINVAL;
+    if (features % 8 != 0 || (reinterpret_cast<uintptr_t>(x) & 15)) return FEWBIT_EALIGN;  // TMA strides
+    EncodeTiled encode = encode_tiled();
+    if (!encode) return (int)cudaErrorNotSupported;
+    cudaStream_t s = (cudaStream_t)stream;
+    int bn, split_k;
+    plan(rows, features, tokens, sm_count(), bn, split_k);
+    if (split_k > 1 && !workspace) return FEWBIT_EINVAL;
+
+    CUtensorMap map;
+    const cuuint64_t dims[2] = {(cuuint64_t)features, (cuuint64_t)std::max<int64_t>(tokens, 1)};
+    const cuuint64_t strides[1] = {(cuuint64_t)features * 2};
+    const cuuint32_t box[2] = {64, 64}, elem[2] = {1, 1};
+    if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(x), dims, strides, box, elem,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return (int)cudaErrorInvalidValue;
+
+    const int64_t kblocks = (tokens + kBlockK - 1) / kBlockK;
+    Params prm;
+    prm.out = split_k > 1 ? static_cast<float *>(workspace) : out;
+    prm.tokens = tokens, prm.features = features, prm.rows = rows, prm.block_rows = bn;
+    prm.kblocks_per_split = (int)((kblocks + split_k - 1) / split_k);
+    prm.split_k = split_k, prm.scale = scale, prm.kind = kind;
+    prm.seed_lo = (uint32_t)seed, prm.seed_hi = (uint32_t)(seed >> 32);
+    prm.off_lo = (uint32_t)offset, prm.off_hi = (uint32_t)(offset >> 32);
+
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    dim3 grid((rows + bn - 1) / bn, (features + kFeaturesPerCta - 1) / kFeaturesPerCta, split_k);
+    sketch_kernel<<<grid, kThreads, kSmemBytes, s>>>(map, prm);
+    note_launch();
+    if (split_k > 1) {
+        const int64_t count = (int64_t)rows * features;
+        reduce_splits_kernel<<<(unsigned)std::min<int64_t>((count + 255) / 256, sm_count() * 8), 256, 0, s>>>(
+            static_cast<const float *>(workspace), out, count, split_k, scale);
+        note_launch();
+    }
+    return (int)cudaGetLastError();
+}
+
+int fewbit_sketch_matrix(void *s_bf16, int rows, int64_t cols, int kind, uint64_t seed, uint64_t offset,
+                         void *stream) {
+    if (!s_bf16 || rows <= 0 || cols <= 0 || (kind != 0 && kind != 1)) return FEWBIT_EINVAL;
+    Params prm{};
+    prm.kind = kind;
+    prm.seed_lo = (uint32_t)seed, prm.seed_hi = (uint32_t)(seed >> 32);
+    prm.off_lo = (uint32_t)offset, prm.off_hi = (uint32_t)(offset >> 32);
+    const int64_t quads = rows * ((cols + 3) / 4);
+    sketch_matrix_kernel<<<(unsigned)std::min<int64_t>((quads + 255) / 256, sm_count() * 16), 256, 0,
+                           (cudaStream_t)stream>>>(static_cast<__nv_bfloat16 *>(s_bf16), rows, cols, prm);
+    note_launch();
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -228,6 +228,39 @@ Tensor quantize_backward(const Tensor &grads, const Tensor &buffer, const Tensor
     return gin;
 }
 
+// ------------------------------------------------ RandomizedLinear projection ----
+// out[rows, D] = scale * S[rows, N] x[N, D], S generated inside the tcgen05 kernel from
+// (seed, offset); replaces randn + matmul of LinearGRPFunc (fewbit/functional/linear.py:133-137).
+
+Tensor sketch(const Tensor &x, int64_t rows, int64_t seed, int64_t offset, int64_t kind, double scale) {
+    TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.is_contiguous(),
+                "fewbit::sketch: expected a contiguous 2-D CUDA tensor [tokens, features]");
+    TORCH_CHECK(x.scalar_type() == torch::kBFloat16, "fewbit::sketch: x must be bfloat16, got ", x.scalar_type());
+    TORCH_CHECK(x.size(1) % 8 == 0, "fewbit::sketch: the feature count must be a multiple of 8, got ", x.size(1));
+    TORCH_CHECK(rows > 0, "fewbit::sketch: rows must be positive");
+    c10::cuda::CUDAGuard guard(x.device());
+    auto stream = at::cuda::getCurrentCUDAStream();
+    Tensor out = torch::empty({rows, x.size(1)}, x.options().dtype(torch::kFloat32));
+    const size_t nbytes = fewbit_sketch_workspace_bytes(x.size(0), (int)x.size(1), (int)rows);
+    Tensor workspace = torch::empty({(int64_t)std::max<size_t>(nbytes, 16)}, x.options().dtype(torch::kUInt8));
+    check_status(fewbit_sketch_forward(x.data_ptr(), out.data_ptr<float>(), workspace.data_ptr(), x.size(0),
+                                       (int)x.size(1), (int)rows, (int)kind, (float)scale, (uint64_t)seed,
+                                       (uint64_t)offset, stream.stream()),
+                 "sketch");
+    return out;
+}
+
+Tensor sketch_matrix(const Tensor &like, int64_t rows, int64_t cols, int64_t seed, int64_t offset, int64_t kind) {
+    TORCH_CHECK(like.is_cuda(), "fewbit::sketch_matrix: `like` must be a CUDA tensor");
+    c10::cuda::CUDAGuard guard(like.device());
+    auto stream = at::cuda::getCurrentCUDAStream();
+    Tensor s = torch::empty({rows, cols}, like.options().dtype(torch::kBFloat16));
+    check_status(fewbit_sketch_matrix(s.data_ptr(), (int)rows, cols, (int)kind, (uint64_t)seed, (uint64_t)offset,
+                                      stream.stream()),
+                 "sketch_matrix");
+    return s;
+}
+
 }  // namespace
 
 // Schemas: verbatim from the reference (fewbit/fewbit.cc:6-37) -- they are the public ABI.
@@ -257,6 +290,10 @@ TORCH_LIBRARY(fewbit, m) {
     m.def("softsign  (Tensor(a!) self, Tensor bounds, Tensor levels) -> Tensor(a!)");
     m.def("tanh      (Tensor(a!) self, Tensor bounds, Tensor levels) -> Tensor(a!)");
     m.def("tanhshrink(Tensor(a!) self, Tensor bounds, Tensor levels) -> Tensor(a!)");
+
+    // Not in the reference: the projection of RandomizedLinear as one operator.
+    m.def("sketch(Tensor x, int rows, int seed, int offset, int kind, float scale) -> Tensor");
+    m.def("sketch_matrix(Tensor like, int rows, int cols, int seed, int offset, int kind) -> Tensor");
 
     // Declared by the reference without any kernel (fewbit/fewbit.cc:37); kept so that the
     // schema set is identical.  Calling it raises NotImplementedError, as in the reference.
@@ -292,4 +329,6 @@ TORCH_LIBRARY_IMPL(fewbit, AutogradCUDA, m) {
 TORCH_LIBRARY_IMPL(fewbit, CUDA, m) {
     m.impl("quantize", quantize);
     m.impl("quantize_backward", quantize_backward);
+    m.impl("sketch", sketch);
+    m.impl("sketch_matrix", sketch_matrix);
 }

@@ -81,6 +81,36 @@ def _linear_owning_output(input_view: T.Tensor, weight: T.Tensor, bias: Optional
     return out
 
 
+SKETCH_KINDS = {'gaussian': 0, 'rademacher': 1}
+
+
+def _native_sketch_available(tensor: T.Tensor, kind: str) -> bool:
+    """CUDA tensors with a feature count the TMA can address go to the tcgen05 kernel."""
+    if tensor.device.type != 'cuda' or kind not in SKETCH_KINDS:
+        return False
+    from .. import NATIVE_ERROR
+    if NATIVE_ERROR is not None:
+        raise RuntimeError(f'fewbit.linear_grp: CUDA tensor given but the operator library '
+                           f'libfewbit.so is not loaded ({NATIVE_ERROR}).')
+    return tensor.shape[-1] % 8 == 0 and tensor.dtype in (T.float32, T.bfloat16)
+
+
+def _native_sketch(view: T.Tensor, rows: int, seed: int, offset: int, kind: str, scale: float) -> T.Tensor:
+    """scale * S @ view  with S generated inside the kernel (fp32 result, [rows, features]).
+    Operands enter the tensor cores as bf16 (fp32 accumulation); the rounding is unbiased and
+    three orders of magnitude below the sketch's own O(1/sqrt(P)) noise."""
+    return T.ops.fewbit.sketch(view.to(T.bfloat16).contiguous(), rows, seed, offset,
+                               SKETCH_KINDS[kind], scale)
+
+
+def _draw_stream(generator: T.Generator):
+    """(seed, offset) identifying one sketch; advances the generator's Philox offset."""
+    seed = generator.initial_seed() & 0x7FFFFFFFFFFFFFFF
+    offset = generator.get_offset()
+    generator.set_offset(offset + 4)
+    return seed, offset
+
+
 class LinearGRPFunc(T.autograd.Function):
 
     @staticmethod
@@ -96,11 +126,23 @@ class LinearGRPFunc(T.autograd.Function):
             raise ValueError('Param proj_dim_min should be not greater than param proj_dim_max.')
 
         generator = generator or _default_generator(input.device)
-        generator_state = generator.get_state()
-
         input_view = input.reshape(-1, input.shape[-1])
         proj_features = calc_proj_dim(input_view.shape[0], proj_dim_ratio, proj_dim, proj_dim_max,
                                       proj_dim_min)
+
+        if _native_sketch_available(input_view, matmul) and generator.device.type == 'cuda':
+            # B200 path: S never exists in memory; (seed, offset) replaces the generator state.
+            seed, offset = _draw_stream(generator)
+            scale = 1.0 / proj_features if matmul == 'gaussian' else 4.0 / proj_features
+            input_proj = _native_sketch(input_view, proj_features, seed, offset, matmul, scale).to(input.dtype)
+            ctx.save_for_backward(input_proj, weight, bias)
+            ctx.proj_features = proj_features
+            ctx.matmul = matmul
+            ctx.stream = (seed, offset)
+            return _linear_owning_output(input_view, weight, bias, input.shape)
+
+        generator_state = generator.get_state()
+        ctx.stream = None
         proj = _sketch_matrix(matmul, proj_features, input_view.shape[0], generator, input.device,
                               input.dtype)
         # E[S^T S] = P I (gaussian) or P/4 I (rademacher): scale so that E[grad_weight] = G^T X,
@@ -124,7 +166,16 @@ class LinearGRPFunc(T.autograd.Function):
         grad_input = grad_weight = grad_bias = None
         if ctx.needs_input_grad[0]:
             grad_input = grad_output @ weight
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and ctx.stream is not None:
+            grad_view = grad_output.reshape(-1, grad_output.shape[-1])
+            if _native_sketch_available(grad_view, ctx.matmul):
+                grad_proj = _native_sketch(grad_view, ctx.proj_features, *ctx.stream, ctx.matmul, 1.0)
+            else:  # feature count the TMA cannot address: same S, materialised
+                proj = T.ops.fewbit.sketch_matrix(grad_view, ctx.proj_features, grad_view.shape[0],
+                                                  *ctx.stream, SKETCH_KINDS[ctx.matmul])
+                grad_proj = proj.float() @ grad_view.float()
+            grad_weight = (grad_proj.T @ input_proj.float()).to(weight.dtype)
+        elif ctx.needs_input_grad[1]:
             generator = T.Generator(ctx.generator_device)
             generator.set_state(ctx.generator_state)
             grad_view = grad_output.reshape(-1, grad_output.shape[-1])

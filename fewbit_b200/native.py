@@ -40,6 +40,9 @@ PROTOTYPES = {
     'fewbit_stepwise_backward_host': (_i, [_i, _vp, _vp, _vp, _i64, _i, _vp, _i, _i64]),
     'fewbit_piecewise_forward_host': (_i, [_i, _i, _vp, _vp, _vp, _i64, _d, _d, _i64]),
     'fewbit_piecewise_backward_host': (_i, [_i, _i, _vp, _vp, _vp, _i64, _d, _i64]),
+    'fewbit_sketch_workspace_bytes': (C.c_size_t, [_i64, _i, _i]),
+    'fewbit_sketch_forward': (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, C.c_float, C.c_uint64, C.c_uint64, _vp]),
+    'fewbit_sketch_matrix': (_i, [_vp, _i, _i64, _i, C.c_uint64, C.c_uint64, _vp]),
     'fewbit_launch_count': (_i64, []),
 }
 
@@ -168,3 +171,29 @@ def piecewise_backward_host(func, state, gout_host, gin_host, p0=0.0, chunk=0):
                                                state.data_ptr(), gout_host.data_ptr(),
                                                gin_host.data_ptr(), gout_host.numel(), p0, chunk),
           'fewbit_piecewise_backward_host')
+
+
+# RandomizedLinear projection (tcgen05): out[P, D] = scale * S[P, N] @ x[N, D], S generated in-kernel.
+
+SKETCH_KINDS = ('gaussian', 'rademacher')
+
+
+def sketch_forward(x, rows, seed, offset, kind='gaussian', scale=1.0, stream=None):
+    """x: [tokens, features] bf16 device tensor -> [rows, features] fp32."""
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.is_contiguous()
+    tokens, features = x.shape
+    out = torch.empty(rows, features, dtype=torch.float32, device=x.device)
+    nbytes = int(lib().fewbit_sketch_workspace_bytes(tokens, features, rows))
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=x.device)
+    check(lib().fewbit_sketch_forward(x.data_ptr(), out.data_ptr(), ws.data_ptr(), tokens, features, rows,
+                                      SKETCH_KINDS.index(kind), scale, seed, offset, _stream(stream)),
+          'fewbit_sketch_forward')
+    return out
+
+
+def sketch_matrix(rows, cols, seed, offset, kind='gaussian', device='cuda', stream=None):
+    """The sketch S itself as [rows, cols] bf16 (tests / diagnostics)."""
+    s = torch.empty(rows, cols, dtype=torch.bfloat16, device=device)
+    check(lib().fewbit_sketch_matrix(s.data_ptr(), rows, cols, SKETCH_KINDS.index(kind), seed, offset,
+                                     _stream(stream)), 'fewbit_sketch_matrix')
+    return s

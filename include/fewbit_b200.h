@@ -128,6 +128,26 @@ FEWBIT_API int fewbit_piecewise_backward_host(int func, int dtype, const uint8_t
                                    const void *gout_host, void *gin_host, int64_t n, double p0,
                                    int64_t chunk_elems);
 
+/*
+ * RandomizedLinear's projection on tcgen05 tensor cores:  out[P, D] = scale * S[P, N] X[N, D]
+ * with the random sketch S generated inside the kernel (never materialised): entry (p, n) is a
+ * pure function of (seed, offset, p, n), so forward and backward see the same S.  Replaces
+ * `proj = randn(P, N); (proj @ input_view) / P` and `proj @ grad_output_view` of
+ * LinearGRPFunc (fewbit/functional/linear.py:133-137, 196-199).
+ *   x         : [tokens, features] bf16, row-major, 16-byte aligned, features % 8 == 0
+ *   out       : [rows, features] fp32
+ *   workspace : fewbit_sketch_workspace_bytes(...) bytes of device memory (split-K partials;
+ *               may be NULL when that is 0)
+ *   kind      : 0 = N(0,1) entries ('gaussian'), 1 = +-1/2 entries ('rademacher')
+ * fewbit_sketch_matrix writes S itself ([rows, cols] bf16) -- for tests and diagnostics only.
+ */
+FEWBIT_API size_t fewbit_sketch_workspace_bytes(int64_t tokens, int features, int rows);
+FEWBIT_API int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t tokens,
+                                     int features, int rows, int kind, float scale, uint64_t seed,
+                                     uint64_t offset, void *stream);
+FEWBIT_API int fewbit_sketch_matrix(void *s_bf16, int rows, int64_t cols, int kind, uint64_t seed,
+                                    uint64_t offset, void *stream);
+
 /* Number of kernels this library has launched in the calling process (for bench.py's
  * `gpu_launches`). */
 FEWBIT_API int64_t fewbit_launch_count(void);

@@ -1,0 +1,113 @@
+"""The tcgen05 projection of RandomizedLinear: out = scale * S @ X with S generated in-kernel.
+
+S is never materialised by the product; `sketch_matrix` reproduces it with the same device
+function so that the kernel can be checked against a plain fp32 torch matmul of the same S
+(tolerance 2e-3 of the result's RMS: bf16 operands are exact in the fp32 products, only the
+accumulation order differs)."""
+import pytest
+import torch
+
+import fewbit_b200 as fewbit
+from fewbit_b200 import native
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def reference(x, rows, seed, offset, kind, scale):
+    s = native.sketch_matrix(rows, x.shape[0], seed, offset, kind, DEV)
+    return (s.float() @ x.float()) * scale, s
+
+
+@pytest.mark.parametrize('kind', ['gaussian', 'rademacher'])
+def test_sketch_matrix_statistics(kind):
+    s = native.sketch_matrix(512, 4096, 1234, 8, kind, DEV).float()
+    again = native.sketch_matrix(512, 4096, 1234, 8, kind, DEV).float()
+    assert torch.equal(s, again)                                   # pure function of (seed, offset)
+    assert not torch.equal(s, native.sketch_matrix(512, 4096, 1234, 12, kind, DEV).float())
+    assert not torch.equal(s, native.sketch_matrix(512, 4096, 1235, 8, kind, DEV).float())
+    # a sub-block is the same function of (p, n): tiling-independent
+    assert torch.equal(s[:100, :1000], native.sketch_matrix(100, 1000, 1234, 8, kind, DEV).float())
+    if kind == 'gaussian':
+        assert abs(s.mean().item()) < 3e-3 and abs(s.var().item() - 1) < 1e-2
+        assert abs((s ** 4).mean().item() - 3) < 0.1               # kurtosis of a normal
+        assert s.abs().max().item() > 4.0                          # tails are there
+    else:
+        assert set(s.unique().tolist()) == {-0.5, 0.5} and abs(s.mean().item()) < 2e-3
+    gram = (s @ s.T) / s.shape[1]
+    var = 1.0 if kind == 'gaussian' else 0.25
+    off = gram - var * torch.eye(512, device=DEV)
+    assert off.abs().max().item() < 0.12 * var                     # rows uncorrelated: |.| ~ var/sqrt(4096)*5
+
+
+SHAPES = [(64, 8, 16), (1000, 72, 50), (4096, 384, 160), (4100, 392, 161), (2048, 768, 333),
+          (16384, 768, 3276), (3000, 3072, 600), (777, 1024, 1)]
+
+
+@pytest.mark.parametrize('tokens,features,rows', SHAPES)
+@pytest.mark.parametrize('kind', ['gaussian', 'rademacher'])
+def test_kernel_matches_matmul_with_the_same_sketch(tokens, features, rows, kind):
+    torch.manual_seed(tokens + features)
+    x = torch.randn(tokens, features, device=DEV).to(torch.bfloat16)
+    scale = 1.0 / rows
+    out = native.sketch_forward(x, rows, 42, 4, kind, scale)
+    want, _ = reference(x, rows, 42, 4, kind, scale)
+    assert out.shape == (rows, features) and out.dtype == torch.float32
+    err = (out - want).abs().max().item()
+    assert err <= 2e-3 * want.pow(2).mean().sqrt().item() + 1e-7, f'max err {err}'
+
+
+def test_operator_and_errors():
+    x = torch.randn(512, 64, device=DEV).to(torch.bfloat16)
+    out = torch.ops.fewbit.sketch(x, 32, 7, 0, 0, 0.5)
+    want, _ = reference(x, 32, 7, 0, 'gaussian', 0.5)
+    assert torch.allclose(out, want, rtol=1e-3, atol=1e-3)
+    with pytest.raises(RuntimeError, match='bfloat16'):
+        torch.ops.fewbit.sketch(x.float(), 32, 7, 0, 0, 1.0)
+    with pytest.raises(RuntimeError, match='multiple of 8'):
+        torch.ops.fewbit.sketch(x[:, :60].contiguous(), 32, 7, 0, 0, 1.0)
+
+
+@pytest.mark.parametrize('kind', ['gaussian', 'rademacher'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_randomized_linear_uses_one_sketch_forward_and_backward(kind, dtype):
+    """grad_weight = (S G)^T (S X) * scale with the SAME S in both passes."""
+    torch.manual_seed(3)
+    layer = fewbit.RandomizedLinear(256, 128, proj_dim=64, matmul=kind,
+                                    generator=torch.Generator(DEV).manual_seed(99)).to(DEV, dtype)
+    x = torch.randn(4, 128, 256, device=DEV, dtype=dtype, requires_grad=True)
+    g = torch.randn(4, 128, 128, device=DEV, dtype=dtype)
+    seed, offset = layer.generator.initial_seed(), layer.generator.get_offset()
+    y = layer(x)
+    assert layer.generator.get_offset() == offset + 4              # the stream advanced
+    y.backward(g)
+    s = native.sketch_matrix(64, 512, seed, offset, kind, DEV).float()
+    xb, gb = x.detach().reshape(512, 256).to(torch.bfloat16).float(), g.reshape(512, 128).to(torch.bfloat16).float()
+    scale = 1 / 64 if kind == 'gaussian' else 4 / 64
+    x_proj = ((s @ xb) * scale).to(dtype).float()
+    want = (s @ gb).T @ x_proj
+    rel = (layer.weight.grad.float() - want).norm() / want.norm()
+    assert rel.item() < (2e-2 if dtype == torch.bfloat16 else 1e-3)
+    ref = torch.nn.functional.linear(x, layer.weight, layer.bias)
+    assert torch.allclose(y, ref, rtol=1e-2, atol=1e-2)
+    assert torch.allclose(x.grad.float(), (g.float().reshape(512, 128) @ layer.weight.float()).view_as(x),
+                          rtol=2e-2, atol=2e-2)
+
+
+def test_randomized_linear_is_unbiased_on_cuda():
+    # the reference's statistical test (fewbit/modules/linear_test.py:71-92) through the kernel
+    torch.manual_seed(42)
+    layer = fewbit.RandomizedLinear(256, 128, proj_dim=64).to(DEV)
+    ref = torch.nn.Linear(256, 128).to(DEV)
+    ref.load_state_dict(layer.state_dict())
+    x = torch.randn(512, 256, device=DEV, requires_grad=True)
+    acc = torch.zeros_like(layer.weight)
+    for _ in range(2048):
+        layer.zero_grad()
+        y = layer(x)
+        y.backward(torch.ones_like(y))
+        acc += layer.weight.grad
+    z = ref(x)
+    z.backward(torch.ones_like(z))
+    err = torch.linalg.norm(acc / 2048 - ref.weight.grad) / torch.linalg.norm(ref.weight.grad)
+    assert err.item() < 0.1
