@@ -2,8 +2,10 @@
 //
 //   X   : [N tokens, D features] bf16, row-major (TMA source; never copied or transposed)
 //   S   : [P, N] random sketch, N(0,1) or +-1/2 entries, NEVER materialised: every element is
-//         a pure function of (seed, offset, p, n) -- Philox4x32-10 keyed by the seed, counter
-//         (n / 4, p, offset) -> four entries -- so forward and backward regenerate the same S.
+//         a pure function of (seed, offset, p, n) -- Philox4x32-10 keyed by the seed; one call
+//         with counter (n / 8, p, offset) gives eight normals (Box-Muller on 16-bit uniforms),
+//         one call with counter (n / 128, p, offset) gives 128 signs -- so forward and backward
+//         regenerate the same S.
 //   out : [P, D] fp32
 // Replaces `proj = randn(P, N); proj_input = (proj @ input_view) / P` and `proj @ grad_output`
 // of the reference (fewbit/functional/linear.py:133-137, 196-199), which writes S (214 MB at
@@ -22,8 +24,10 @@
 // The TMEM lane = feature orientation also makes the epilogue store coalesced: for a fixed
 // sketch row the 32 lanes of a warp hold 32 consecutive features.
 //
-// CTA = 8 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-7 generate
-// S; warps 4-7 then run the epilogue (tcgen05.ld -> scale -> global).  Three-stage mbarrier
+// CTA = 16 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-15
+// generate S (the generation is the most expensive part: ~17 instructions and 2 MUFU ops per
+// normal, so it gets 14 of the 16 warps and several independent Philox chains per thread);
+// warps 4-7 then run the epilogue (tcgen05.ld -> scale -> global).  Three-stage mbarrier
 // pipeline: full_x (TMA bytes), full_s (generator warps), empty (tcgen05.commit).
 // Grid = (ceil(P / BN), ceil(D / 384), split_k); split-K partials are reduced by a tiny kernel.
 #include <cuda.h>
@@ -42,7 +46,7 @@ int sm_count();
 
 namespace sketch {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr int kStages = 3;
 constexpr int kBlockK = 64;            // tokens per stage
 constexpr int kFeaturesPerCta = 384;   // 3 MMA M-blocks of 128
@@ -52,7 +56,8 @@ constexpr int kXStageBytes = (kFeaturesPerCta / 64) * kBoxBytes;   // 49152
 constexpr int kSStageBytes = kMaxRows * 128;                  // 20480: BN rows x 64 bf16
 constexpr int kStageBytes = kXStageBytes + kSStageBytes;
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* alignment */ + 256 /* barriers */;
-constexpr int kGeneratorWarps = 6;
+constexpr int kGeneratorWarps = 14;
+constexpr int kGeneratorThreads = kGeneratorWarps * 32;
 constexpr int kTmemColumns = 512;
 
 // ---------------------------------------------------------------------------- PTX ----
@@ -139,31 +144,45 @@ struct Philox {
     }
 };
 
-__device__ __forceinline__ float unit_open(uint32_t bits) {  // (0, 1), 23 random bits
-    return __uint_as_float(0x3f800000u | (bits >> 9)) - (1.0f - 5.9604645e-8f);
+__device__ __forceinline__ float lg2_approx(float v) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
 }
-
-// Entries S[p][4q .. 4q+3] as two packed bf16x2 words.  kind 0: N(0,1) by Box-Muller on the
-// four Philox words; kind 1: +-1/2 from their top bits.
-__device__ __forceinline__ uint2 sketch_quad(const Philox &rng, uint32_t q, uint32_t p, uint32_t off_lo,
-                                             uint32_t off_hi, int kind) {
-    const uint4 r = rng(make_uint4(q, p, off_lo, off_hi));
-    float z0, z1, z2, z3;
-    if (kind == 0) {
-        const float r0 = sqrtf(-1.3862943611198906f * __log2f(unit_open(r.x)));   // sqrt(-2 ln u)
-        const float r1 = sqrtf(-1.3862943611198906f * __log2f(unit_open(r.z)));
-        float s0, c0, s1, c1;
-        __sincosf(6.283185307179586f * unit_open(r.y), &s0, &c0);
-        __sincosf(6.283185307179586f * unit_open(r.w), &s1, &c1);
-        z0 = r0 * c0, z1 = r0 * s0, z2 = r1 * c1, z3 = r1 * s1;
-    } else {
-        z0 = (r.x >> 31) ? 0.5f : -0.5f, z1 = (r.y >> 31) ? 0.5f : -0.5f;
-        z2 = (r.z >> 31) ? 0.5f : -0.5f, z3 = (r.w >> 31) ? 0.5f : -0.5f;
-    }
-    uint2 out;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(out.x) : "f"(z1), "f"(z0));
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(out.y) : "f"(z3), "f"(z2));
-    return out;
+__device__ __forceinline__ float sqrt_approx(float v) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// (h + 1/2) / 65536 in (0, 1) from 16 random bits: mantissa trick, no integer->float convert.
+__device__ __forceinline__ float unit16(uint32_t h) {
+    return __uint_as_float(0x3f800000u | (h << 7)) - (1.0f - 7.62939453125e-6f);
+}
+// Two normals from one 32-bit word: Box-Muller with a 16-bit radius and a 16-bit angle.
+__device__ __forceinline__ uint32_t normal_pair(uint32_t word) {
+    const float radius = sqrt_approx(-1.3862943611198906f * lg2_approx(unit16(word & 0xffffu)));   // sqrt(-2 ln u)
+    const float angle = 6.283185307179586f * unit16(word >> 16);
+    return pack_bf16(radius * __cosf(angle), radius * __sinf(angle));
+}
+// kind 0: entries S[p][8o .. 8o+7] (eight normals) as four packed bf16x2 words.
+__device__ __forceinline__ uint4 normal_octet(const Philox &rng, uint32_t o, uint32_t p, uint32_t off_lo,
+                                              uint32_t off_hi) {
+    const uint4 r = rng(make_uint4(o, p, off_lo, off_hi));
+    return make_uint4(normal_pair(r.x), normal_pair(r.y), normal_pair(r.z), normal_pair(r.w));
+}
+// kind 1: 128 signs S[p][128c .. 128c+127]; bit b of word w is entry 32w + b.
+__device__ __forceinline__ uint4 sign_block(const Philox &rng, uint32_t c, uint32_t p, uint32_t off_lo,
+                                            uint32_t off_hi) {
+    return rng(make_uint4(c, p, off_lo, off_hi));
+}
+// Two consecutive sign bits -> packed bf16x2 of +-1/2 (0x3f00 = 0.5, sign bit set for bit = 0).
+__device__ __forceinline__ uint32_t sign_pair(uint32_t bits) {
+    return 0x3f003f00u | ((~bits & 1u) << 15) | ((~bits & 2u) << 30);
 }
 
 // --------------------------------------------------------------------------- kernel ----
@@ -269,26 +288,48 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     } else {
         // -------------------------------------------------------------- generators ----
         const Philox rng{prm.seed_lo, prm.seed_hi};
-        const int gt = threadIdx.x - 64;                       // 0 .. 191
-        const int quads = bn * (kBlockK / 4);                  // per stage: bn rows x 16 quads
+        const int gt = threadIdx.x - 64;                       // 0 .. 447
         for (int it = 0; it < iters; ++it) {
             const int s = it % kStages;
             mbar_wait(empty(s), ((it / kStages) & 1) ^ 1);
             uint8_t *tile = smem + s * kStageBytes + kXStageBytes;
-            const uint32_t q0 = (uint32_t)((kb_begin + it) * (kBlockK / 4));
-            for (int i = gt; i < quads; i += kGeneratorWarps * 32) {
-                const int row = i >> 4, q = i & 15;
-                const uint2 v = sketch_quad(rng, q0 + q, (uint32_t)(p0 + row), prm.off_lo, prm.off_hi, prm.kind);
-                // K-major SW128: 16-byte chunk index XOR (row mod 8)
-                const int chunk = (q >> 1) ^ (row & 7);
-                *reinterpret_cast<uint2 *>(tile + (row >> 3) * 1024 + (row & 7) * 128 + chunk * 16 + (q & 1) * 8) = v;
+            const int64_t kb = kb_begin + it;
+            if (prm.kind == 0) {
+                // One Philox call = 8 normals = one 16-byte chunk of a 128-byte K-major row.
+                // K-major SW128: chunk index XOR (row mod 8).  Up to 3 chunks per thread
+                // (160 rows x 8 chunks over 448 threads), independent chains interleave.
+                const int chunks = bn * 8;
+#pragma unroll
+                for (int j = 0; j < (kMaxRows * 8 + kGeneratorThreads - 1) / kGeneratorThreads; ++j) {
+                    const int i = gt + j * kGeneratorThreads;
+                    if (i < chunks) {
+                        const int row = i >> 3, o = i & 7;
+                        const uint4 v = normal_octet(rng, (uint32_t)(kb * 8 + o), (uint32_t)(p0 + row),
+                                                     prm.off_lo, prm.off_hi);
+                        *reinterpret_cast<uint4 *>(tile + (row >> 3) * 1024 + (row & 7) * 128 + ((o ^ (row & 7)) << 4)) = v;
+                    }
+                }
+            } else {
+                // One Philox call = 128 signs; a 64-token stage uses half of it.  One row per
+                // thread: 64 entries = 128 bytes = the whole (swizzled) row.
+                for (int row = gt; row < bn; row += kGeneratorThreads) {
+                    const uint4 r = sign_block(rng, (uint32_t)(kb >> 1), (uint32_t)(p0 + row), prm.off_lo, prm.off_hi);
+                    const uint32_t w0 = (kb & 1) ? r.z : r.x, w1 = (kb & 1) ? r.w : r.y;
+                    uint8_t *base = tile + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        const uint32_t bits = (o < 4 ? w0 : w1) >> ((o & 3) * 8);
+                        *reinterpret_cast<uint4 *>(base + ((o ^ (row & 7)) << 4)) =
+                            make_uint4(sign_pair(bits), sign_pair(bits >> 2), sign_pair(bits >> 4), sign_pair(bits >> 6));
+                    }
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(full_s(s));
         }
         // ---------------------------------------------------------------- epilogue ----
-        if (warp >= 4) {
+        if (warp >= 4 && warp < 8) {
             mbar_wait(accum_full, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int quarter = warp & 3;                       // TMEM lanes [32q, 32q + 32)
@@ -335,14 +376,23 @@ __global__ void reduce_splits_kernel(const float *partials, float *out, int64_t 
 // S itself, for tests and diagnostics only (the product never materialises it).
 __global__ void sketch_matrix_kernel(__nv_bfloat16 *s, int rows, int64_t cols, Params prm) {
     const Philox rng{prm.seed_lo, prm.seed_hi};
-    const int64_t quads_per_row = (cols + 3) / 4;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * quads_per_row;
+    const int64_t octets_per_row = (cols + 7) / 8;
+    uint16_t *dst = reinterpret_cast<uint16_t *>(s);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * octets_per_row;
          i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t p = i / quads_per_row, q = i % quads_per_row;
-        const uint2 v = sketch_quad(rng, (uint32_t)q, (uint32_t)p, prm.off_lo, prm.off_hi, prm.kind);
-        const uint16_t e[4] = {(uint16_t)v.x, (uint16_t)(v.x >> 16), (uint16_t)v.y, (uint16_t)(v.y >> 16)};
-        for (int j = 0; j < 4; ++j)
-            if (4 * q + j < cols) reinterpret_cast<uint16_t *>(s)[p * cols + 4 * q + j] = e[j];
+        const int64_t p = i / octets_per_row, o = i % octets_per_row;
+        uint32_t w[4];
+        if (prm.kind == 0) {
+            const uint4 v = normal_octet(rng, (uint32_t)o, (uint32_t)p, prm.off_lo, prm.off_hi);
+            w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
+        } else {
+            const uint4 r = sign_block(rng, (uint32_t)(o >> 4), (uint32_t)p, prm.off_lo, prm.off_hi);
+            const uint32_t words[4] = {r.x, r.y, r.z, r.w};
+            const uint32_t bits = words[(o >> 2) & 3] >> ((o & 3) * 8);
+            w[0] = sign_pair(bits), w[1] = sign_pair(bits >> 2), w[2] = sign_pair(bits >> 4), w[3] = sign_pair(bits >> 6);
+        }
+        for (int j = 0; j < 8; ++j)
+            if (8 * o + j < cols) dst[p * cols + 8 * o + j] = (uint16_t)(w[j >> 1] >> ((j & 1) * 16));
     }
 }
 
@@ -365,9 +415,7 @@ static EncodeTiled encode_tiled() {
     return fn;
 }
 
-// Pick BN (multiple of 16, <= 160) and split_k: minimise  waves * (time of one CTA), where a
-// CTA's main loop costs ~BN per 64-token block (S generation and MMA both scale with BN) plus a
-// fixed prologue/epilogue worth ~6 blocks at BN = 160.
+// Pick BN (multiple of 16, <= 160) and split_k: minimise  waves * (time of one CTA).
 static void plan(int rows, int features, int64_t tokens, int sms, int &bn, int &split_k) {
     const int dtiles = (features + kFeaturesPerCta - 1) / kFeaturesPerCta;
     const int64_t kblocks = std::max<int64_t>(1, (tokens + kBlockK - 1) / kBlockK);
@@ -378,7 +426,9 @@ static void plan(int rows, int features, int64_t tokens, int sms, int &bn, int &
         for (int sk = 1; sk <= 8 && sk <= kblocks; ++sk) {
             const int64_t ctas = (int64_t)ptiles * dtiles * sk;
             const int64_t waves = (ctas + sms - 1) / sms;
-            const double per_cta = (double)((kblocks + sk - 1) / sk) * cand + 6.0 * 160.0;
+            // per 64-token block: S generation ~11 cycles per row, but never less than the
+            // ~1100 cycles the 48 KB X tile needs to arrive from L2
+            const double per_cta = (double)((kblocks + sk - 1) / sk) * std::max(cand * 11.0, 1100.0) + 8000.0;
             const double cost = (double)waves * per_cta * (1.0 + 0.01 * (sk - 1));
             if (cost < best) best = cost, bn = cand, split_k = sk;
         }
@@ -454,8 +504,8 @@ int fewbit_sketch_matrix(void *s_bf16, int rows, int64_t cols, int kind, uint64_
     prm.kind = kind;
     prm.seed_lo = (uint32_t)seed, prm.seed_hi = (uint32_t)(seed >> 32);
     prm.off_lo = (uint32_t)offset, prm.off_hi = (uint32_t)(offset >> 32);
-    const int64_t quads = rows * ((cols + 3) / 4);
-    sketch_matrix_kernel<<<(unsigned)std::min<int64_t>((quads + 255) / 256, sm_count() * 16), 256, 0,
+    const int64_t octets = rows * ((cols + 7) / 8);
+    sketch_matrix_kernel<<<(unsigned)std::min<int64_t>((octets + 255) / 256, sm_count() * 16), 256, 0,
                            (cudaStream_t)stream>>>(static_cast<__nv_bfloat16 *>(s_bf16), rows, cols, prm);
     note_launch();
     return (int)cudaGetLastError();
