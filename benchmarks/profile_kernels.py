@@ -1,5 +1,5 @@
 """Launch each hot kernel a few times at benchmark size -- the target of the ncu captures
-(`ncu --set full -k regex:tiles_kernel ... python benchmarks/profile_kernels.py`)."""
+(`ncu --set full -k regex:'tiles_kernel|sketch_kernel' ... python benchmarks/profile_kernels.py`)."""
 import sys
 from pathlib import Path
 
@@ -39,4 +39,10 @@ if which in ('all', 'gelu'):
             native.stepwise_forward('gelu', x, y, state, 3, bounds)
             native.stepwise_backward(state, g, gin, 3, levels)
         torch.cuda.synchronize()
+
+if which in ('all', 'sketch'):
+    x = torch.randn(16384, 768, device=dev).to(torch.bfloat16)
+    for _ in range(reps):
+        native.sketch_forward(x, 3276, 1, 0, 'gaussian', 1.0 / 3276)
+    torch.cuda.synchronize()
 print('done')
