@@ -160,15 +160,57 @@ template <typename T, int B> struct Bucketizer<T, B, false> {
 };
 
 // =====================================================================================
-// Continuous activations.  Formulas are the ones ATen's CUDA kernels use in fp32 opmath
-// (that is what the reference's test compares against: functional/activations_test.py:88-89),
-// evaluated with the accurate libdevice functions; bf16 inputs are widened to fp32 and the
-// result is rounded once.  Reference lambdas: fewbit/cuda/codec.cu:517-653.
+// Continuous activations.  fp32: the expressions ATen's CUDA kernels use in fp32 opmath (that is
+// what the reference's test compares against: functional/activations_test.py:88-89) with the
+// accurate libdevice functions (mish and softplus/beta=1 rearranged, still within 4 ulp).
+// bf16: inputs are widened to fp32, evaluated with the MUFU-based forms below (a bf16 kernel
+// moves half the bytes per element, so libdevice-grade math would make it compute-bound at
+// 26-50 % of HBM speed) and rounded once.  Reference lambdas: fewbit/cuda/codec.cu:517-653.
 // =====================================================================================
+
+// MUFU-based building blocks of the bf16 paths.  A bf16 result keeps 8 significant bits, so
+// the ~2^-22 relative error of ex2/rcp/lg2.approx is invisible after the final rounding; what
+// matters is the ALGEBRA: forms without cancellation, so the relative error stays ~1e-6
+// everywhere (tests: <= 1 bf16 ulp from the fp32-exact result, and equal to it for > 99 %).
+__device__ __forceinline__ float rcp_approx(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float lg2_approx(float v) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+__device__ __forceinline__ float fast_exp(float x) { return ex2_approx(x * kLog2e); }
+// log(1 + e^z): for z < -8 the sum 1 + e^z loses e^z's digits, and log1p(e^z) = e^z (1 - e^z/2 ..)
+__device__ __forceinline__ float fast_log1p_exp(float z) {
+    const float e = fast_exp(z);
+    return z < -8.0f ? e : kLn2 * lg2_approx(1.0f + e);
+}
+// e^z - 1 without cancellation near zero (|z| < 2^-9: z + z^2/2).
+__device__ __forceinline__ float fast_expm1(float z) {
+    return fabsf(z) < 0.001953125f ? fmaf(0.5f * z, z, z) : fast_exp(z) - 1.0f;
+}
+// tanh: odd polynomial below 1/4 (relative error 3e-7), 1 - 2/(1 + e^{2|x|}) above.
+__device__ __forceinline__ float fast_tanh(float x) {
+    const float a = fabsf(x), x2 = x * x;
+    const float small = x * fmaf(x2, fmaf(x2, fmaf(x2, -0.05396825397f, 0.13333333333f), -0.33333333333f), 1.0f);
+    const float big = copysignf(fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(a * (2.0f * kLog2e))), 1.0f), x);
+    return a < 0.25f ? small : big;
+}
 
 struct EluFamily {  // celu / elu / selu:  x > 0 ? x*pos : expm1(x*in_scale)*neg
     float pos, neg, in_scale;
     template <typename T> __device__ __forceinline__ float eval(float x) const {
+        if constexpr (sizeof(T) == 2) return x > 0.0f ? x * pos : fast_expm1(x * in_scale) * neg;
         return x > 0.0f ? x * pos : expm1f(x * in_scale) * neg;
     }
 };
@@ -192,16 +234,6 @@ struct SeluFn : EluFamily {  // codec.cu:588-600
 //     erfc(t) = s * 2^(P(s) - log2(e) t^2),   s = 1 / (1 + t/2),   t = |x| / sqrt 2
 // with a degree-5 P fitted by tools/fit_gelu.py (0.1 % of results differ from the fp32-exact
 // bf16 rounding, by one bf16 ulp): 11 FMA-pipe ops + 2 MUFU, no ALU-pipe op.
-__device__ __forceinline__ float rcp_approx(float v) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
-__device__ __forceinline__ float ex2_approx(float v) {
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
 struct GeluFn {  // codec.cu:539-544 (x * normcdf(x))
     __host__ GeluFn(double, double) {}
     template <typename T> __device__ __forceinline__ float eval(float x) const {
@@ -237,44 +269,76 @@ struct HardswishFn {  // codec.cu:546-564
 struct LogSigmoidFn {  // codec.cu:566-576
     __host__ LogSigmoidFn(double, double) {}
     template <typename T> __device__ __forceinline__ float eval(float x) const {
+        if constexpr (sizeof(T) == 2) return fminf(0.0f, x) - fast_log1p_exp(-fabsf(x));
         return fminf(0.0f, x) - log1pf(expf(-fabsf(x)));
     }
 };
 struct MishFn {  // codec.cu:578-586
+    // tanh(log(1 + e)) = ((1+e)^2 - 1) / ((1+e)^2 + 1) = n / (n + 2) with n = e (e + 2), e = e^x:
+    // one exponential and one division instead of exp, log1p and tanh (57 -> ~25 instructions),
+    // all terms positive (no cancellation).  x is capped at 20 in the exponential, where
+    // n / (n + 2) is already 1 in fp32.
     __host__ MishFn(double, double) {}
     template <typename T> __device__ __forceinline__ float eval(float x) const {
-        return x * tanhf(log1pf(expf(x)));
+        if constexpr (sizeof(T) == 2) {
+            const float e = fast_exp(fminf(x, 20.0f)), n = e * (e + 2.0f);
+            return x * n * rcp_approx(n + 2.0f);
+        }
+        const float e = expf(fminf(x, 20.0f)), n = e * (e + 2.0f);
+        return x * (n / (n + 2.0f));
     }
 };
 struct SigmoidFn {  // codec.cu:602-607
     __host__ SigmoidFn(double, double) {}
     template <typename T> __device__ __forceinline__ float eval(float x) const {
+        if constexpr (sizeof(T) == 2) return rcp_approx(1.0f + fast_exp(-x));
         return 1.0f / (1.0f + expf(-x));
     }
 };
 struct SiluFn {  // codec.cu:609-614
     __host__ SiluFn(double, double) {}
-    template <typename T> __device__ __forceinline__ float eval(float x) const { return x / (1.0f + expf(-x)); }
+    template <typename T> __device__ __forceinline__ float eval(float x) const {
+        if constexpr (sizeof(T) == 2) return x * rcp_approx(1.0f + fast_exp(-x));
+        return x / (1.0f + expf(-x));
+    }
 };
 struct SoftplusFn {  // codec.cu:616-632
-    float beta, threshold;
-    __host__ SoftplusFn(double b, double t) : beta((float)b), threshold((float)t) {}
+    float beta, threshold, inv_beta;
+    bool unit_beta;
+    __host__ SoftplusFn(double b, double t)
+        : beta((float)b), threshold((float)t), inv_beta((float)(1.0 / b)), unit_beta((float)b == 1.0f) {}
     template <typename T> __device__ __forceinline__ float eval(float x) const {
         const float bx = x * beta;
-        return bx > threshold ? x : log1pf(expf(bx)) / beta;
+        if constexpr (sizeof(T) == 2) return bx > threshold ? x : fast_log1p_exp(bx) * inv_beta;
+        const float soft = log1pf(expf(bx));
+        return bx > threshold ? x : (unit_beta ? soft : soft / beta);   // x / 1 is exact: skip it
     }
 };
 struct SoftsignFn {  // codec.cu:634-639
     __host__ SoftsignFn(double, double) {}
-    template <typename T> __device__ __forceinline__ float eval(float x) const { return x / (1.0f + fabsf(x)); }
+    template <typename T> __device__ __forceinline__ float eval(float x) const {
+        if constexpr (sizeof(T) == 2) return x * rcp_approx(1.0f + fabsf(x));
+        return x / (1.0f + fabsf(x));
+    }
 };
 struct TanhFn {  // codec.cu:641-646
     __host__ TanhFn(double, double) {}
-    template <typename T> __device__ __forceinline__ float eval(float x) const { return tanhf(x); }
+    template <typename T> __device__ __forceinline__ float eval(float x) const {
+        if constexpr (sizeof(T) == 2) return fast_tanh(x);
+        return tanhf(x);
+    }
 };
 struct TanhshrinkFn {  // codec.cu:648-653
     __host__ TanhshrinkFn(double, double) {}
-    template <typename T> __device__ __forceinline__ float eval(float x) const { return x - tanhf(x); }
+    template <typename T> __device__ __forceinline__ float eval(float x) const {
+        if constexpr (sizeof(T) == 2) {
+            // x - tanh(x) cancels below 1/4: use the series x^3 (1/3 - 2 x^2/15 + 17 x^4/315) there
+            const float x2 = x * x;
+            const float small = x * x2 * fmaf(x2, fmaf(x2, 0.05396825397f, -0.13333333333f), 0.33333333333f);
+            return fabsf(x) < 0.25f ? small : x - fast_tanh(x);
+        }
+        return x - tanhf(x);
+    }
 };
 
 // Forward op of a continuous activation: y = fn(x), code = bucket(x), eight values at a time.

@@ -90,6 +90,25 @@ def test_forward_matches_torch_cuda_kernels(name, dtype):
     assert torch.all(err <= tol), f'{name}: max err {err.max().item():.3e}'
 
 
+@pytest.mark.parametrize('name', CONTINOUS)
+def test_bf16_results_are_the_fp32_exact_rounding(name):
+    """The bf16 kernels use short MUFU-based evaluations; after rounding they must be
+    indistinguishable from ATen's fp32 math rounded once: never more than one bf16 ulp away,
+    and bit-identical for > 99 % of N(0, 2^2) inputs."""
+    torch.manual_seed(17)
+    x = (torch.randn(1 << 22, device=DEV) * 2).to(torch.bfloat16)
+    args = {'celu': (1.5, ), 'elu': (0.7, ), 'softplus': (2.0, 10.0)}.get(name, ())
+    ref = (getattr(F, name, None) or getattr(torch, name))(x.float(), *args).to(torch.bfloat16)
+    y = getattr(FF, name)(x.clone(), *args, bits=3)
+    same = (y.view(torch.int16) == ref.view(torch.int16)) | ((y == 0) & (ref == 0))
+    assert same.float().mean().item() > 0.99, f'{name}: only {same.float().mean().item():.4f} identical'
+    steps = (y.view(torch.int16).int() - ref.view(torch.int16).int()).abs()
+    # beyond one ulp only where fp32 formulas themselves carry an absolute error (gelu's 1 + erf
+    # cancels in the negative tail: ATen's own result is off by up to 1.5e-7 there)
+    far = (steps > 1) & ((y.float() - ref.float()).abs() > 2.5e-7)
+    assert not far.any(), f'{name}: {int(far.sum())} results more than one bf16 ulp away'
+
+
 # ---- operator semantics -------------------------------------------------------------------
 
 def test_in_place_and_only_codes_are_saved():
