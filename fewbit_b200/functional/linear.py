@@ -174,7 +174,8 @@ class LinearGRPFunc(T.autograd.Function):
                 proj = T.ops.fewbit.sketch_matrix(grad_view, ctx.proj_features, grad_view.shape[0],
                                                   *ctx.stream, SKETCH_KINDS[ctx.matmul])
                 grad_proj = proj.float() @ grad_view.float()
-            grad_weight = (grad_proj.T @ input_proj.float()).to(weight.dtype)
+            # (S G)^T (S X): a small [out, P] x [P, in] product in the layer's own precision
+            grad_weight = grad_proj.to(input_proj.dtype).T @ input_proj
         elif ctx.needs_input_grad[1]:
             generator = T.Generator(ctx.generator_device)
             generator.set_state(ctx.generator_state)
