@@ -30,12 +30,22 @@
 // warps 4-7 then run the epilogue (tcgen05.ld -> scale -> global).  Three-stage mbarrier
 // pipeline: full_x (TMA bytes), full_s (generator warps), empty (tcgen05.commit).
 // Grid = (ceil(P / BN), ceil(D / 384), split_k); split-K partials are reduced by a tiny kernel.
+//
+// Sharing S across feature tiles.  Generating S costs about twice the MMA time, and CTAs that
+// differ only in their feature tile need the very same S tile.  They are launched as a
+// thread-block cluster (1, C, 1), C in {1, 2, 4, 8}: CTA r generates rows [r BN/C, (r+1) BN/C) of
+// each stage into its own shared memory and pushes that block to every peer with
+// cp.async.bulk.shared::cluster (async proxy; completes transaction bytes on the PEER's full_s
+// barrier, so the tensor core sees the data without any generic-proxy hand-over).  A stage may
+// be overwritten only when every CTA of the cluster has consumed it: tcgen05.commit multicasts
+// its arrival to the `empty` barrier of all C CTAs.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/fewbit_b200.h"
 
@@ -102,6 +112,33 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {   // shared::cta -> shared::cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes,
+                                                  uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            dst_cluster),
+        "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_cluster(uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"(mask)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -198,6 +235,7 @@ struct Params {
     float scale;         // applied here only when split_k == 1
     uint32_t seed_lo, seed_hi, off_lo, off_hi;
     int kind;
+    int cluster;         // C: CTAs along grid.y that share one S tile
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -226,11 +264,14 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     auto x_stage = [&](int s) { return smem_addr(smem + s * kStageBytes); };
     auto s_stage = [&](int s) { return smem_addr(smem + s * kStageBytes + kXStageBytes); };
 
+    const int cluster = prm.cluster;
+    const uint32_t rank = cluster > 1 ? cluster_rank() : 0;
+    const int my_rows = bn / cluster;                       // rows of each S tile this CTA generates
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full_x(s), 1);
-            mbar_init(full_s(s), kGeneratorWarps);
-            mbar_init(empty(s), 1);
+            mbar_init(full_s(s), kGeneratorWarps + (cluster > 1 ? 1 : 0));   // + the expect_tx arrival
+            mbar_init(empty(s), cluster);                                    // one commit per CTA
         }
         mbar_init(accum_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -243,6 +284,7 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (cluster > 1) cluster_sync();          // peers' barriers exist before anyone signals them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
@@ -253,6 +295,7 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
                 const int s = it % kStages;
                 mbar_wait(empty(s), ((it / kStages) & 1) ^ 1);
                 mbar_expect_tx(full_x(s), nboxes * kBoxBytes);
+                if (cluster > 1) mbar_expect_tx(full_s(s), (cluster - 1) * my_rows * 128);   // peers' blocks
                 const int token = (int)((kb_begin + it) * kBlockK);
                 for (int b = 0; b < nboxes; ++b)
                     tma_load_2d(x_stage(s) + b * kBoxBytes, &x_map, d0 + 64 * b, token, full_x(s));
@@ -281,7 +324,9 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
                         umma_bf16(tmem_base + m * kMaxRows, desc_a, desc_b, idesc, (it | k) != 0);
                     }
                 }
-                umma_commit(empty(s));        // smem slot reusable once these MMAs have read it
+                // smem slot reusable once these MMAs have read it -- in every CTA of the cluster
+                if (cluster > 1) umma_commit_cluster(empty(s), (uint16_t)((1u << cluster) - 1));
+                else umma_commit(empty(s));
             }
             umma_commit(accum_full);          // accumulators complete
         }
@@ -294,16 +339,17 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
             mbar_wait(empty(s), ((it / kStages) & 1) ^ 1);
             uint8_t *tile = smem + s * kStageBytes + kXStageBytes;
             const int64_t kb = kb_begin + it;
+            const int row0 = (int)rank * my_rows;              // this CTA's block of the tile
             if (prm.kind == 0) {
                 // One Philox call = 8 normals = one 16-byte chunk of a 128-byte K-major row.
                 // K-major SW128: chunk index XOR (row mod 8).  Up to 3 chunks per thread
                 // (160 rows x 8 chunks over 448 threads), independent chains interleave.
-                const int chunks = bn * 8;
+                const int chunks = my_rows * 8;
 #pragma unroll
                 for (int j = 0; j < (kMaxRows * 8 + kGeneratorThreads - 1) / kGeneratorThreads; ++j) {
                     const int i = gt + j * kGeneratorThreads;
                     if (i < chunks) {
-                        const int row = i >> 3, o = i & 7;
+                        const int row = row0 + (i >> 3), o = i & 7;
                         const uint4 v = normal_octet(rng, (uint32_t)(kb * 8 + o), (uint32_t)(p0 + row),
                                                      prm.off_lo, prm.off_hi);
                         *reinterpret_cast<uint4 *>(tile + (row >> 3) * 1024 + (row & 7) * 128 + ((o ^ (row & 7)) << 4)) = v;
@@ -312,9 +358,10 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
             } else {
                 // One Philox call = 128 signs; a 64-token stage uses half of it.  One row per
                 // thread: 64 entries = 128 bytes = the whole (swizzled) row.
-                for (int row = gt; row < bn; row += kGeneratorThreads) {
-                    const uint4 r = sign_block(rng, (uint32_t)(kb >> 1), (uint32_t)(p0 + row), prm.off_lo, prm.off_hi);
-                    const uint32_t w0 = (kb & 1) ? r.z : r.x, w1 = (kb & 1) ? r.w : r.y;
+                for (int r = gt; r < my_rows; r += kGeneratorThreads) {
+                    const int row = row0 + r;
+                    const uint4 w = sign_block(rng, (uint32_t)(kb >> 1), (uint32_t)(p0 + row), prm.off_lo, prm.off_hi);
+                    const uint32_t w0 = (kb & 1) ? w.z : w.x, w1 = (kb & 1) ? w.w : w.y;
                     uint8_t *base = tile + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll
                     for (int o = 0; o < 8; ++o) {
@@ -325,6 +372,17 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
+            if (cluster > 1) {
+                // all generator threads have written (and fenced) this CTA's block: push it to the peers
+                asm volatile("bar.sync 1, %0;" ::"n"(kGeneratorThreads) : "memory");
+                if (gt == 0) {
+                    const uint32_t block = smem_addr(tile) + row0 * 128;
+                    for (uint32_t peer = 0; peer < (uint32_t)cluster; ++peer)
+                        if (peer != rank)
+                            bulk_copy_to_peer(map_to_cta(block, peer), block, my_rows * 128,
+                                              map_to_cta(full_s(s), peer));
+                }
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(full_s(s));
         }
@@ -357,6 +415,7 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (cluster > 1) cluster_sync();          // nobody leaves while peers may still signal it
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"(kTmemColumns));
@@ -415,20 +474,32 @@ static EncodeTiled encode_tiled() {
     return fn;
 }
 
-// Pick BN (multiple of 16, <= 160) and split_k: minimise  waves * (time of one CTA).
-static void plan(int rows, int features, int64_t tokens, int sms, int &bn, int &split_k) {
+// Pick the cluster size C (feature tiles that share S), BN (multiple of 16 and of 8 C, <= 160)
+// and split_k: minimise  waves * (time of one CTA).
+static void plan(int rows, int features, int64_t tokens, int sms, int &bn, int &split_k, int &cluster) {
     const int dtiles = (features + kFeaturesPerCta - 1) / kFeaturesPerCta;
     const int64_t kblocks = std::max<int64_t>(1, (tokens + kBlockK - 1) / kBlockK);
+    // Measured on B200 (profiles/r01_sketch_kernel.md): pairs help a little at D = 768 (131 -> 123 us);
+    // clusters of 8 lose to independent CTAs at D = 3072 (569 vs 492 us: 8-CTA placement leaves
+    // SMs idle and the lock-step `empty` barrier couples eight pipelines), so C is capped at 2.
+    cluster = dtiles % 2 == 0 ? 2 : 1;
+    if (dtiles > 2) cluster = 1;
+    if (const char *env = std::getenv("FEWBIT_B200_SKETCH_CLUSTER")) {   // A/B runs: cap the cluster size
+        const int cap = std::atoi(env);
+        while (cap >= 1 && cluster > cap) cluster /= 2;
+    }
     double best = 1e300;
-    bn = 160, split_k = 1;
+    bn = 64, split_k = 1;
     for (int cand = 160; cand >= 64; cand -= 16) {
+        if ((cand / 8) % cluster != 0) continue;
         const int ptiles = (rows + cand - 1) / cand;
         for (int sk = 1; sk <= 8 && sk <= kblocks; ++sk) {
             const int64_t ctas = (int64_t)ptiles * dtiles * sk;
             const int64_t waves = (ctas + sms - 1) / sms;
-            // per 64-token block: S generation ~11 cycles per row, but never less than the
-            // ~1100 cycles the 48 KB X tile needs to arrive from L2
-            const double per_cta = (double)((kblocks + sk - 1) / sk) * std::max(cand * 11.0, 1100.0) + 8000.0;
+            // per 64-token block: S generation ~11 cycles per generated row, MMA 6 cycles per row,
+            // and never less than the ~1100 cycles the 48 KB X tile needs to arrive from L2
+            const double block = std::max({cand * 11.0 / cluster, cand * 6.0, 1100.0});
+            const double per_cta = (double)((kblocks + sk - 1) / sk) * block + 8000.0;
             const double cost = (double)waves * per_cta * (1.0 + 0.01 * (sk - 1));
             if (cost < best) best = cost, bn = cand, split_k = sk;
         }
@@ -444,8 +515,8 @@ using namespace fewbit::sketch;
 extern "C" {
 
 size_t fewbit_sketch_workspace_bytes(int64_t tokens, int features, int rows) {
-    int bn, split_k;
-    plan(rows, features, tokens, sm_count(), bn, split_k);
+    int bn, split_k, cluster;
+    plan(rows, features, tokens, sm_count(), bn, split_k, cluster);
     return split_k > 1 ? (size_t)split_k * rows * features * sizeof(float) : 0;
 }
 
@@ -457,8 +528,8 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
     EncodeTiled encode = encode_tiled();
     if (!encode) return (int)cudaErrorNotSupported;
     cudaStream_t s = (cudaStream_t)stream;
-    int bn, split_k;
-    plan(rows, features, tokens, sm_count(), bn, split_k);
+    int bn, split_k, cluster;
+    plan(rows, features, tokens, sm_count(), bn, split_k, cluster);
     if (split_k > 1 && !workspace) return FEWBIT_EINVAL;
 
     CUtensorMap map;
@@ -475,7 +546,7 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
     prm.out = split_k > 1 ? static_cast<float *>(workspace) : out;
     prm.tokens = tokens, prm.features = features, prm.rows = rows, prm.block_rows = bn;
     prm.kblocks_per_split = (int)((kblocks + split_k - 1) / split_k);
-    prm.split_k = split_k, prm.scale = scale, prm.kind = kind;
+    prm.split_k = split_k, prm.scale = scale, prm.kind = kind, prm.cluster = cluster;
     prm.seed_lo = (uint32_t)seed, prm.seed_hi = (uint32_t)(seed >> 32);
     prm.off_lo = (uint32_t)offset, prm.off_hi = (uint32_t)(offset >> 32);
 
@@ -485,8 +556,17 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    dim3 grid((rows + bn - 1) / bn, (features + kFeaturesPerCta - 1) / kFeaturesPerCta, split_k);
-    sketch_kernel<<<grid, kThreads, kSmemBytes, s>>>(map, prm);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((rows + bn - 1) / bn, (features + kFeaturesPerCta - 1) / kFeaturesPerCta, split_k);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1, attr[0].val.clusterDim.y = cluster, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    cudaError_t launched = cudaLaunchKernelEx(&cfg, sketch_kernel, map, prm);
+    if (launched != cudaSuccess) return (int)launched;
     note_launch();
     if (split_k > 1) {
         const int64_t count = (int64_t)rows * features;
