@@ -4,6 +4,8 @@ bench-linear.py, measured the reference's way: benchmark/benchmark.py:165-188).
 
     python benchmarks/roberta_step.py [--batch 128] [--seq 128] [--steps 5] [--dtype fp32|bf16]
                                       [--variants vanilla,gelu3,rand0.2,both] [--json out.json]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           benchmarks/roberta_step.py --ddp --variant both        # configs[4]: data parallel
 
 Random-init `RobertaForSequenceClassification` (no network: no checkpoint, no GLUE), synthetic
 `input_ids`, AdamW lr 2e-5 wd 0.01 (bench-roberta.py:84-93).  Each variant runs in a child
@@ -56,12 +58,22 @@ def build_model(variant: str, dtype):
 def child(args):
     import torch
     sys.path.insert(0, str(ROOT))
-    torch.manual_seed(0)
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    if args.ddp:
+        # Data parallel: every rank runs the same per-GPU batch (weak scaling); the quantized
+        # activations and the sketches stay local to the GPU that produced them, the only
+        # communication is DDP's gradient all-reduce over NCCL (plumbing).
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)))
+        dist.init_process_group('nccl')
+    torch.manual_seed(rank)
     dtype = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
     torch.cuda.init()
     base = torch.cuda.memory_allocated()
     model, swapped = build_model(args.variant, dtype)
     model.train()
+    if args.ddp:
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[torch.cuda.current_device()])
     opt = torch.optim.AdamW(model.parameters(), lr=2e-5, weight_decay=0.01)
     ids = torch.randint(0, 50265, (args.batch, args.seq), device='cuda')
     labels = torch.randint(0, 2, (args.batch, ), device='cuda')
@@ -81,9 +93,19 @@ def child(args):
             times.append(a.elapsed_time(b))
     peak = torch.cuda.max_memory_allocated() - base
     params = sum(p.numel() for p in model.parameters())
-    print(json.dumps({'variant': args.variant, 'step_ms': statistics.median(times),
-                      'peak_gib': peak / 2 ** 30, 'params_m': params / 1e6, 'swapped': swapped,
-                      'loss_first': losses[0], 'loss_last': losses[-1]}))
+    step_ms = statistics.median(times)
+    if args.ddp:
+        import torch.distributed as dist
+        t = torch.tensor([step_ms, peak / 2 ** 30], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms, peak = t[0].item(), t[1].item() * 2 ** 30
+    if rank == 0:
+        print(json.dumps({'variant': args.variant, 'step_ms': step_ms, 'peak_gib': peak / 2 ** 30,
+                          'params_m': params / 1e6, 'swapped': swapped, 'loss_first': losses[0],
+                          'loss_last': losses[-1], 'world_size': world,
+                          'tokens_per_s': world * args.batch * args.seq / (step_ms / 1e3)}))
+    if args.ddp:
+        dist.destroy_process_group()
 
 
 def main():
@@ -95,7 +117,10 @@ def main():
     ap.add_argument('--variants', default='vanilla,gelu3,rand0.2,both')
     ap.add_argument('--variant', default=None)
     ap.add_argument('--json', default=None)
+    ap.add_argument('--ddp', action='store_true', help='run under torchrun with DistributedDataParallel')
     args = ap.parse_args()
+    if args.ddp and not args.variant:
+        args.variant = 'both'
     if args.variant:
         return child(args)
     results = []

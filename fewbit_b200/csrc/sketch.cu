@@ -550,11 +550,14 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
     prm.seed_lo = (uint32_t)seed, prm.seed_hi = (uint32_t)(seed >> 32);
     prm.off_lo = (uint32_t)offset, prm.off_hi = (uint32_t)(offset >> 32);
 
-    static bool configured = false;
-    if (!configured) {
+    // function attributes live in the device's context: set once per device
+    static bool configured[64] = {};
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= 64) device = 0;
+    if (!configured[device]) {
         cudaError_t e = cudaFuncSetAttribute(sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured[device] = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((rows + bn - 1) / bn, (features + kFeaturesPerCta - 1) / kFeaturesPerCta, split_k);

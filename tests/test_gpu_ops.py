@@ -259,3 +259,52 @@ def test_randomized_linear_on_cuda():
     layer.zero_grad(); layer(x).sum().backward(); a = layer.weight.grad.clone()
     layer.zero_grad(); layer(x).sum().backward()
     assert not torch.equal(a, layer.weight.grad)
+
+
+def test_kernels_are_cuda_graph_capturable():
+    """No hidden synchronisation or allocation in the C ABI: a forward + backward pair can be
+    captured into a CUDA graph and replayed on new data (DESIGN: streams and graphs)."""
+    from fewbit_b200 import native
+    n = 1 << 20
+    borders, levels = store.get('gelu', 3, DEV, torch.bfloat16)
+    bounds, levels = borders[1:-1].contiguous(), levels.contiguous()
+    x = torch.empty(n, dtype=torch.bfloat16, device=DEV)
+    g = torch.empty(n, dtype=torch.bfloat16, device=DEV)
+    y, gin = torch.empty_like(x), torch.empty_like(g)
+    state, mask = native.new_state(x, 3), native.new_state(x, 1)
+    x.normal_(0, 2); g.normal_()
+    native.stepwise_forward('gelu', x, y, state, 3, bounds)       # warm up outside the capture
+    native.piecewise_forward('relu', x, y, mask)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        native.stepwise_forward('gelu', x, y, state, 3, bounds)
+        native.stepwise_backward(state, g, gin, 3, levels)
+        native.piecewise_forward('relu', x, y, mask)
+    for seed in (1, 2):
+        torch.manual_seed(seed)
+        x.normal_(0, 2); g.normal_()
+        graph.replay()
+        torch.cuda.synchronize()
+        codes = torch.searchsorted(bounds.float(), x.float())
+        assert torch.equal(gin, (levels.float()[codes] * g.float()).to(torch.bfloat16))
+        assert torch.equal(y, torch.relu(x))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_second_device_is_respected():
+    """Device guard + current stream of the tensor's device (reference bug C-8: it launches on
+    the current device's legacy stream whatever the tensor's device is)."""
+    dev1 = 'cuda:1'
+    x = (torch.randn(3, 1000, 64, device=dev1) * 2)
+    h = x.clone().requires_grad_()
+    y = FF.gelu(h * 1.0, bits=3)                   # current device stays cuda:0
+    y.sum().backward()
+    assert y.device == h.grad.device == torch.device(dev1)
+    assert torch.allclose(y, F.gelu(x), atol=1e-6)
+    borders, levels = store.get('gelu', 3, dev1, torch.float32)
+    assert torch.equal(h.grad, levels[torch.searchsorted(borders[1:-1].contiguous(), x)])
+    layer = fewbit.RandomizedLinear(64, 32, proj_dim_ratio=0.25).to(dev1)
+    out = layer(x.requires_grad_())
+    out.sum().backward()
+    assert layer.weight.grad.device == torch.device(dev1) and torch.isfinite(layer.weight.grad).all()
