@@ -31,14 +31,18 @@
 // pipeline: full_x (TMA bytes), full_s (generator warps), empty (tcgen05.commit).
 // Grid = (ceil(P / BN), ceil(D / 384), split_k); split-K partials are reduced by a tiny kernel.
 //
-// Sharing S across feature tiles.  Generating S costs about twice the MMA time, and CTAs that
-// differ only in their feature tile need the very same S tile.  They are launched as a
-// thread-block cluster (1, C, 1), C in {1, 2, 4, 8}: CTA r generates rows [r BN/C, (r+1) BN/C) of
-// each stage into its own shared memory and pushes that block to every peer with
-// cp.async.bulk.shared::cluster (async proxy; completes transaction bytes on the PEER's full_s
-// barrier, so the tensor core sees the data without any generic-proxy hand-over).  A stage may
-// be overwritten only when every CTA of the cluster has consumed it: tcgen05.commit multicasts
-// its arrival to the `empty` barrier of all C CTAs.
+// Sharing operands inside a thread-block cluster (Cx, Cy, 1), Cx, Cy in {1, 2}:
+//  * along y (feature tiles): generating S costs about twice the MMA time, and CTAs that differ
+//    only in their feature tile need the very same S tile.  CTA ry generates rows
+//    [ry BN/Cy, (ry+1) BN/Cy) of each stage into its own shared memory and pushes that block to
+//    its y-peer with cp.async.bulk.shared::cluster (async proxy; completes transaction bytes on
+//    the PEER's full_s barrier, so the tensor core sees the data without a generic-proxy
+//    hand-over).
+//  * along x (sketch-row tiles): CTAs that differ only in their row tile stream the very same X
+//    tiles, and re-reading X from L2 once per row tile is what bounds the kernel when S is cheap
+//    (Rademacher).  Each CTA loads every Cx-th TMA box and multicasts it to its x-peers.
+// A stage may be overwritten only when every CTA of the cluster has consumed it: tcgen05.commit
+// multicasts its arrival to the `empty` barrier of all CTAs of the cluster.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -105,6 +109,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         "l"(map), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const CUtensorMap *map, int c0, int c1,
+                                                      uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
+        : "memory");
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                           uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -114,9 +126,14 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ uint32_t cluster_rank() {
+__device__ __forceinline__ uint32_t cluster_cta_x() {
     uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    asm volatile("mov.u32 %0, %%cluster_ctaid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_cta_y() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctaid.y;" : "=r"(r));
     return r;
 }
 __device__ __forceinline__ void cluster_sync() {
@@ -235,7 +252,8 @@ struct Params {
     float scale;         // applied here only when split_k == 1
     uint32_t seed_lo, seed_hi, off_lo, off_hi;
     int kind;
-    int cluster;         // C: CTAs along grid.y that share one S tile
+    int cluster_x;       // CTAs along grid.x that share X tiles (TMA multicast)
+    int cluster_y;       // CTAs along grid.y that share one generated S tile
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -264,14 +282,14 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     auto x_stage = [&](int s) { return smem_addr(smem + s * kStageBytes); };
     auto s_stage = [&](int s) { return smem_addr(smem + s * kStageBytes + kXStageBytes); };
 
-    const int cluster = prm.cluster;
-    const uint32_t rank = cluster > 1 ? cluster_rank() : 0;
-    const int my_rows = bn / cluster;                       // rows of each S tile this CTA generates
+    const int cx = prm.cluster_x, cy = prm.cluster_y, cluster = cx * cy;
+    const uint32_t rx = cx > 1 ? cluster_cta_x() : 0, ry = cy > 1 ? cluster_cta_y() : 0;   // rank = rx + ry * cx
+    const int my_rows = bn / cy;                            // rows of each S tile this CTA generates
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full_x(s), 1);
-            mbar_init(full_s(s), kGeneratorWarps + (cluster > 1 ? 1 : 0));   // + the expect_tx arrival
-            mbar_init(empty(s), cluster);                                    // one commit per CTA
+            mbar_init(full_s(s), kGeneratorWarps + (cy > 1 ? 1 : 0));   // + the expect_tx arrival
+            mbar_init(empty(s), cluster);                               // one commit per CTA
         }
         mbar_init(accum_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -294,11 +312,17 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
             for (int it = 0; it < iters; ++it) {
                 const int s = it % kStages;
                 mbar_wait(empty(s), ((it / kStages) & 1) ^ 1);
-                mbar_expect_tx(full_x(s), nboxes * kBoxBytes);
-                if (cluster > 1) mbar_expect_tx(full_s(s), (cluster - 1) * my_rows * 128);   // peers' blocks
+                mbar_expect_tx(full_x(s), nboxes * kBoxBytes);                         // all boxes, whoever loads them
+                if (cy > 1) mbar_expect_tx(full_s(s), (cy - 1) * my_rows * 128);       // the y-peer's block
                 const int token = (int)((kb_begin + it) * kBlockK);
-                for (int b = 0; b < nboxes; ++b)
-                    tma_load_2d(x_stage(s) + b * kBoxBytes, &x_map, d0 + 64 * b, token, full_x(s));
+                if (cx > 1) {
+                    const uint16_t mask = (uint16_t)(((1u << cx) - 1u) << (ry * cx));  // my row of the cluster
+                    for (int b = (int)rx; b < nboxes; b += cx)
+                        tma_load_2d_multicast(x_stage(s) + b * kBoxBytes, &x_map, d0 + 64 * b, token, full_x(s), mask);
+                } else {
+                    for (int b = 0; b < nboxes; ++b)
+                        tma_load_2d(x_stage(s) + b * kBoxBytes, &x_map, d0 + 64 * b, token, full_x(s));
+                }
             }
         }
     } else if (warp == 1) {
@@ -339,7 +363,7 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
             mbar_wait(empty(s), ((it / kStages) & 1) ^ 1);
             uint8_t *tile = smem + s * kStageBytes + kXStageBytes;
             const int64_t kb = kb_begin + it;
-            const int row0 = (int)rank * my_rows;              // this CTA's block of the tile
+            const int row0 = (int)ry * my_rows;                // this CTA's block of the tile
             if (prm.kind == 0) {
                 // One Philox call = 8 normals = one 16-byte chunk of a 128-byte K-major row.
                 // K-major SW128: chunk index XOR (row mod 8).  Up to 3 chunks per thread
@@ -372,15 +396,15 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
-            if (cluster > 1) {
-                // all generator threads have written (and fenced) this CTA's block: push it to the peers
+            if (cy > 1) {
+                // all generator threads have written (and fenced) this CTA's block: push it to the y-peers
                 asm volatile("bar.sync 1, %0;" ::"n"(kGeneratorThreads) : "memory");
                 if (gt == 0) {
                     const uint32_t block = smem_addr(tile) + row0 * 128;
-                    for (uint32_t peer = 0; peer < (uint32_t)cluster; ++peer)
-                        if (peer != rank)
-                            bulk_copy_to_peer(map_to_cta(block, peer), block, my_rows * 128,
-                                              map_to_cta(full_s(s), peer));
+                    for (uint32_t y = 0; y < (uint32_t)cy; ++y)
+                        if (y != ry)
+                            bulk_copy_to_peer(map_to_cta(block, rx + y * cx), block, my_rows * 128,
+                                              map_to_cta(full_s(s), rx + y * cx));
                 }
             }
             __syncwarp();
@@ -474,31 +498,34 @@ static EncodeTiled encode_tiled() {
     return fn;
 }
 
-// Pick the cluster size C (feature tiles that share S), BN (multiple of 16 and of 8 C, <= 160)
-// and split_k: minimise  waves * (time of one CTA).
-static void plan(int rows, int features, int64_t tokens, int sms, int &bn, int &split_k, int &cluster) {
+// Pick the cluster (Cx row tiles sharing X by TMA multicast, Cy feature tiles sharing one
+// generated S tile), BN (multiple of 16 and of 8 Cy, <= 160) and split_k: minimise
+// waves * (time of one CTA).  Measured on B200 (profiles/r01_sketch_kernel.md): clusters of 8
+// along y lose to independent CTAs at D = 3072 (8-CTA placement leaves SMs idle and the lock-step
+// `empty` barrier couples eight pipelines), so both axes are capped at 2.
+static void plan(int rows, int features, int64_t tokens, int sms, int &bn, int &split_k, int &cx, int &cy) {
     const int dtiles = (features + kFeaturesPerCta - 1) / kFeaturesPerCta;
     const int64_t kblocks = std::max<int64_t>(1, (tokens + kBlockK - 1) / kBlockK);
-    // Measured on B200 (profiles/r01_sketch_kernel.md): pairs help a little at D = 768 (131 -> 123 us);
-    // clusters of 8 lose to independent CTAs at D = 3072 (569 vs 492 us: 8-CTA placement leaves
-    // SMs idle and the lock-step `empty` barrier couples eight pipelines), so C is capped at 2.
-    cluster = dtiles % 2 == 0 ? 2 : 1;
-    if (dtiles > 2) cluster = 1;
-    if (const char *env = std::getenv("FEWBIT_B200_SKETCH_CLUSTER")) {   // A/B runs: cap the cluster size
-        const int cap = std::atoi(env);
-        while (cap >= 1 && cluster > cap) cluster /= 2;
+    // Default from the A/B runs in profiles/r01_sketch_kernel.md: S sharing between the two feature
+    // tiles of D = 768 helps (133 -> 123 us); X multicast does not (159 us), L2 is not the limiter.
+    cy = dtiles == 2 ? 2 : 1;
+    cx = 1;
+    if (const char *env = std::getenv("FEWBIT_B200_SKETCH_CLUSTER")) {   // A/B runs: "<cx><cy>", e.g. 11, 21, 12, 22
+        const int v = std::atoi(env);
+        if (v / 10 >= 1 && v / 10 <= 2) cx = rows > 160 ? v / 10 : 1;
+        if (v % 10 >= 1 && v % 10 <= 2) cy = std::min(cy, v % 10);
     }
     double best = 1e300;
     bn = 64, split_k = 1;
     for (int cand = 160; cand >= 64; cand -= 16) {
-        if ((cand / 8) % cluster != 0) continue;
-        const int ptiles = (rows + cand - 1) / cand;
+        if ((cand / 8) % cy != 0) continue;
+        const int ptiles = ((rows + cand - 1) / cand + cx - 1) / cx * cx;
         for (int sk = 1; sk <= 8 && sk <= kblocks; ++sk) {
             const int64_t ctas = (int64_t)ptiles * dtiles * sk;
             const int64_t waves = (ctas + sms - 1) / sms;
             // per 64-token block: S generation ~11 cycles per generated row, MMA 6 cycles per row,
-            // and never less than the ~1100 cycles the 48 KB X tile needs to arrive from L2
-            const double block = std::max({cand * 11.0 / cluster, cand * 6.0, 1100.0});
+            // and the 48 KB X tile needs ~1100 cycles to arrive from L2 (half with multicast)
+            const double block = std::max({cand * 11.0 / cy, cand * 6.0, 1100.0 / cx});
             const double per_cta = (double)((kblocks + sk - 1) / sk) * block + 8000.0;
             const double cost = (double)waves * per_cta * (1.0 + 0.01 * (sk - 1));
             if (cost < best) best = cost, bn = cand, split_k = sk;
@@ -515,8 +542,8 @@ using namespace fewbit::sketch;
 extern "C" {
 
 size_t fewbit_sketch_workspace_bytes(int64_t tokens, int features, int rows) {
-    int bn, split_k, cluster;
-    plan(rows, features, tokens, sm_count(), bn, split_k, cluster);
+    int bn, split_k, cx, cy;
+    plan(rows, features, tokens, sm_count(), bn, split_k, cx, cy);
     return split_k > 1 ? (size_t)split_k * rows * features * sizeof(float) : 0;
 }
 
@@ -528,8 +555,8 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
     EncodeTiled encode = encode_tiled();
     if (!encode) return (int)cudaErrorNotSupported;
     cudaStream_t s = (cudaStream_t)stream;
-    int bn, split_k, cluster;
-    plan(rows, features, tokens, sm_count(), bn, split_k, cluster);
+    int bn, split_k, cx, cy;
+    plan(rows, features, tokens, sm_count(), bn, split_k, cx, cy);
     if (split_k > 1 && !workspace) return FEWBIT_EINVAL;
 
     CUtensorMap map;
@@ -546,7 +573,7 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
     prm.out = split_k > 1 ? static_cast<float *>(workspace) : out;
     prm.tokens = tokens, prm.features = features, prm.rows = rows, prm.block_rows = bn;
     prm.kblocks_per_split = (int)((kblocks + split_k - 1) / split_k);
-    prm.split_k = split_k, prm.scale = scale, prm.kind = kind, prm.cluster = cluster;
+    prm.split_k = split_k, prm.scale = scale, prm.kind = kind, prm.cluster_x = cx, prm.cluster_y = cy;
     prm.seed_lo = (uint32_t)seed, prm.seed_hi = (uint32_t)(seed >> 32);
     prm.off_lo = (uint32_t)offset, prm.off_hi = (uint32_t)(offset >> 32);
 
@@ -560,13 +587,14 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
         configured[device] = true;
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((rows + bn - 1) / bn, (features + kFeaturesPerCta - 1) / kFeaturesPerCta, split_k);
+    // grid.x rounded up to whole clusters: surplus CTAs compute rows >= P, which are never stored
+    cfg.gridDim = dim3(((rows + bn - 1) / bn + cx - 1) / cx * cx, (features + kFeaturesPerCta - 1) / kFeaturesPerCta, split_k);
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = kSmemBytes;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1, attr[0].val.clusterDim.y = cluster, attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = cx, attr[0].val.clusterDim.y = cy, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
     cudaError_t launched = cudaLaunchKernelEx(&cfg, sketch_kernel, map, prm);
     if (launched != cudaSuccess) return (int)launched;
