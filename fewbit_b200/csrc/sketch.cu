@@ -254,6 +254,8 @@ struct Params {
     int kind;
     int cluster_x;       // CTAs along grid.x that share X tiles (TMA multicast)
     int cluster_y;       // CTAs along grid.y that share one generated S tile
+    int debug;           // timing experiments only (results are garbage): 1 = skip generating S,
+                         // 2 = skip loading X, 4 = skip issuing MMAs
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -312,6 +314,7 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
             for (int it = 0; it < iters; ++it) {
                 const int s = it % kStages;
                 mbar_wait(empty(s), ((it / kStages) & 1) ^ 1);
+                if (prm.debug & 2) { mbar_arrive(full_x(s)); continue; }
                 mbar_expect_tx(full_x(s), nboxes * kBoxBytes);                         // all boxes, whoever loads them
                 if (cy > 1) mbar_expect_tx(full_s(s), (cy - 1) * my_rows * 128);       // the y-peer's block
                 const int token = (int)((kb_begin + it) * kBlockK);
@@ -338,7 +341,7 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
                 mbar_wait(full_s(s), parity);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
+                for (int k = 0; k < ((prm.debug & 4) ? 0 : kBlockK / 16); ++k) {
                     // B: rows of 128 B (64 tokens), 8-row groups 1024 B apart; +32 B per 16 tokens.
                     const uint64_t desc_b = smem_desc(s_stage(s) + 32 * k, 16, 1024);
                     for (int m = 0; m < nblocks; ++m) {
@@ -364,7 +367,8 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
             uint8_t *tile = smem + s * kStageBytes + kXStageBytes;
             const int64_t kb = kb_begin + it;
             const int row0 = (int)ry * my_rows;                // this CTA's block of the tile
-            if (prm.kind == 0) {
+            if (prm.debug & 1) {
+            } else if (prm.kind == 0) {
                 // One Philox call = 8 normals = one 16-byte chunk of a 128-byte K-major row.
                 // K-major SW128: chunk index XOR (row mod 8).  Up to 3 chunks per thread
                 // (160 rows x 8 chunks over 448 threads), independent chains interleave.
@@ -380,16 +384,19 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
                     }
                 }
             } else {
-                // One Philox call = 128 signs; a 64-token stage uses half of it.  One row per
-                // thread: 64 entries = 128 bytes = the whole (swizzled) row.
-                for (int r = gt; r < my_rows; r += kGeneratorThreads) {
-                    const int row = row0 + r;
+                // One Philox call = 128 signs; a 64-token stage uses half of it (two words), and
+                // each task expands one word = 32 tokens = four 16-byte chunks of a row, so that
+                // 2 x rows tasks keep most generator threads busy (the call is recomputed by the
+                // two tasks of a row: cheaper than leaving 3/4 of the threads idle).
+                for (int task = gt; task < 2 * my_rows; task += kGeneratorThreads) {
+                    const int row = row0 + (task >> 1), half = task & 1;
                     const uint4 w = sign_block(rng, (uint32_t)(kb >> 1), (uint32_t)(p0 + row), prm.off_lo, prm.off_hi);
-                    const uint32_t w0 = (kb & 1) ? w.z : w.x, w1 = (kb & 1) ? w.w : w.y;
+                    const uint32_t word = (kb & 1) ? (half ? w.w : w.z) : (half ? w.y : w.x);
                     uint8_t *base = tile + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll
-                    for (int o = 0; o < 8; ++o) {
-                        const uint32_t bits = (o < 4 ? w0 : w1) >> ((o & 3) * 8);
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t bits = word >> (c * 8);
+                        const int o = half * 4 + c;
                         *reinterpret_cast<uint4 *>(base + ((o ^ (row & 7)) << 4)) =
                             make_uint4(sign_pair(bits), sign_pair(bits >> 2), sign_pair(bits >> 4), sign_pair(bits >> 6));
                     }
@@ -574,6 +581,8 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
     prm.tokens = tokens, prm.features = features, prm.rows = rows, prm.block_rows = bn;
     prm.kblocks_per_split = (int)((kblocks + split_k - 1) / split_k);
     prm.split_k = split_k, prm.scale = scale, prm.kind = kind, prm.cluster_x = cx, prm.cluster_y = cy;
+    prm.debug = 0;
+    if (const char *env = std::getenv("FEWBIT_B200_SKETCH_DEBUG")) prm.debug = std::atoi(env);
     prm.seed_lo = (uint32_t)seed, prm.seed_hi = (uint32_t)(seed >> 32);
     prm.off_lo = (uint32_t)offset, prm.off_hi = (uint32_t)(offset >> 32);
 
