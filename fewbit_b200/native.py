@@ -7,11 +7,10 @@ Every wrapper raises ``RuntimeError`` on a non-zero status -- nothing falls back
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import torch
-
-import os
 
 # FEWBIT_B200_LIBRARY: load another build of the kernels (tuning sweeps only).
 LIBRARY = Path(os.environ.get('FEWBIT_B200_LIBRARY') or Path(__file__).with_name('libfewbit_b200.so'))
