@@ -4,7 +4,8 @@
 // argument checks, allocation of the packed state, autograd bookkeeping (mark_dirty +
 // save_for_backward, as ContinousCudaFunction fewbit/cuda/activation.cc:337-382 and the
 // eight *CudaFunction classes :23-330), and one call into the C ABI (include/fewbit_b200.h)
-// per pass.  No arithmetic happens here and there is no CPU path: CUDA tensors only.
+// per pass.  CUDA tensors only ever reach the CUDA kernels (no fallback); CPU tensors are served
+// for the three operators the reference serves on CPU (gelu, quantize, quantize_backward).
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/library.h>
@@ -261,6 +262,85 @@ Tensor sketch_matrix(const Tensor &like, int64_t rows, int64_t cols, int64_t see
     return s;
 }
 
+// --------------------------------------------------- CPU tensors (dispatch key CPU) ----
+// The reference serves CPU tensors for gelu / quantize / quantize_backward
+// (fewbit/cpu/gelu.cc:7-76).  Same semantics here -- ATen for the values and the bucket search,
+// and the exact-`bits` LSB-first stream -- but packing and unpacking run in parallel over octets
+// (the reference's Deflate / Inflate are single-threaded by construction).  This is the CPU side
+// of the device switch, not a fallback: CUDA tensors never come here.
+
+int bits_of(int64_t nlevels) { return fewbit_bits_for_levels((int)nlevels); }
+
+Tensor pack_codes_cpu(const Tensor &codes, int bits) {   // codes: contiguous int32
+    const int64_t n = codes.numel();
+    Tensor state = torch::zeros({(int64_t)fewbit_state_bytes(n, bits)}, torch::kUInt8);
+    const int32_t *src = codes.data_ptr<int32_t>();
+    uint8_t *dst = state.data_ptr<uint8_t>();
+    const int64_t noctets = (n + 7) / 8, nbytes = state.numel();
+    at::parallel_for(0, noctets, 4096, [&](int64_t begin, int64_t end) {
+        for (int64_t o = begin; o < end; ++o) {
+            uint64_t octet = 0;
+            for (int j = 0; j < 8 && 8 * o + j < n; ++j)
+                octet |= (uint64_t)((uint32_t)src[8 * o + j] & ((1u << bits) - 1u)) << (bits * j);
+            for (int k = 0; k < bits && o * bits + k < nbytes; ++k) dst[o * bits + k] = (uint8_t)(octet >> (8 * k));
+        }
+    });
+    return state;
+}
+
+Tensor unpack_codes_cpu(const Tensor &state, int64_t n, int bits) {   // -> int64 codes
+    Tensor codes = torch::empty({n}, torch::kInt64);
+    const uint8_t *src = state.data_ptr<uint8_t>();
+    int64_t *dst = codes.data_ptr<int64_t>();
+    const int64_t noctets = (n + 7) / 8, nbytes = state.numel();
+    at::parallel_for(0, noctets, 4096, [&](int64_t begin, int64_t end) {
+        for (int64_t o = begin; o < end; ++o) {
+            uint64_t octet = 0;
+            for (int k = 0; k < bits && o * bits + k < nbytes; ++k) octet |= (uint64_t)src[o * bits + k] << (8 * k);
+            for (int j = 0; j < 8 && 8 * o + j < n; ++j) dst[8 * o + j] = (int64_t)((octet >> (bits * j)) & ((1u << bits) - 1u));
+        }
+    });
+    return codes;
+}
+
+std::tuple<Tensor, Tensor> quantize_cpu(const Tensor &inputs, const Tensor &bounds) {
+    TORCH_CHECK(bounds.dim() == 1 && bounds.numel() >= 1 && bounds.numel() <= 255, "fewbit: 1..255 bounds expected");
+    Tensor x = inputs.contiguous();
+    Tensor outputs = torch::gelu(x);
+    Tensor codes = torch::searchsorted(bounds.to(x.scalar_type()).contiguous(), x, /*out_int32=*/true);
+    return {outputs, pack_codes_cpu(codes.reshape({-1}).contiguous(), bits_of(bounds.numel() + 1))};
+}
+
+Tensor quantize_backward_cpu(const Tensor &grads, const Tensor &buffer, const Tensor &levels) {
+    TORCH_CHECK(buffer.scalar_type() == torch::kUInt8 && buffer.is_contiguous(),
+                "fewbit::quantize_backward: `buffer` must be a contiguous uint8 tensor");
+    const int bits = bits_of(levels.numel());
+    TORCH_CHECK((size_t)buffer.numel() >= fewbit_state_bytes(grads.numel(), bits),
+                "fewbit::quantize_backward: `buffer` is too short");
+    Tensor codes = unpack_codes_cpu(buffer, grads.numel(), bits).view(grads.sizes());
+    return levels.to(grads.scalar_type()).index({codes}) * grads;
+}
+
+class GeluCpuFunction : public torch::autograd::Function<GeluCpuFunction> {
+public:
+    static Tensor forward(AutogradContext *ctx, const Tensor &inputs, const Tensor &bounds, const Tensor &levels) {
+        TORCH_CHECK(bounds.numel() + 1 == levels.numel(),
+                    "fewbit: size of `bounds` should be lesser than size of `levels` by one, got ",
+                    bounds.numel(), " and ", levels.numel());
+        auto [outputs, buffer] = quantize_cpu(inputs, bounds);
+        ctx->save_for_backward({buffer, levels});
+        return outputs;   // out of place on CPU, exactly as the reference
+    }
+    static variable_list backward(AutogradContext *ctx, variable_list grad_output) {
+        auto saved = ctx->get_saved_variables();
+        return {quantize_backward_cpu(grad_output[0].contiguous(), saved[0], saved[1]), Tensor(), Tensor()};
+    }
+};
+
+Tensor gelu_cpu(Tensor &self, const Tensor &bounds, const Tensor &levels) {
+    return GeluCpuFunction::apply(self, bounds, levels);
+}
+
 }  // namespace
 
 // Schemas: verbatim from the reference (fewbit/fewbit.cc:6-37) -- they are the public ABI.
@@ -324,6 +404,13 @@ TORCH_LIBRARY_IMPL(fewbit, AutogradCUDA, m) {
     m.impl("softsign", softsign);
     m.impl("tanh", tanh_);
     m.impl("tanhshrink", tanhshrink);
+}
+
+// As the reference: only gelu and the quantize pair exist for CPU tensors (fewbit/cpu/gelu.cc:74-76).
+TORCH_LIBRARY_IMPL(fewbit, AutogradCPU, m) { m.impl("gelu", gelu_cpu); }
+TORCH_LIBRARY_IMPL(fewbit, CPU, m) {
+    m.impl("quantize", quantize_cpu);
+    m.impl("quantize_backward", quantize_backward_cpu);
 }
 
 TORCH_LIBRARY_IMPL(fewbit, CUDA, m) {

@@ -103,9 +103,38 @@ def test_operator_library_schemas():
 
 
 def test_cpu_tensor_is_rejected_by_the_cuda_operators():
+    """As in the reference, only gelu / quantize / quantize_backward exist for CPU tensors
+    (fewbit/cpu/gelu.cc:74-76); every other operator is CUDA-only and says so."""
     import torch
     import fewbit_b200  # noqa: F401
     with pytest.raises(NotImplementedError):
         torch.ops.fewbit.relu(torch.zeros(8))
     with pytest.raises(NotImplementedError):
-        torch.ops.fewbit.gelu(torch.zeros(8), torch.zeros(7), torch.zeros(8))
+        torch.ops.fewbit.silu(torch.zeros(8), torch.zeros(7), torch.zeros(8))
+
+
+def test_cpu_operators_reproduce_the_reference(golden_ops):
+    """torch.ops.fewbit.quantize / quantize_backward / gelu on CPU tensors against the fixtures
+    produced by the unmodified reference CPU ops: packed bytes, gradients and values bit for bit
+    (both sides use ATen's gelu and searchsorted; the packer here is parallel, the stream the same)."""
+    import numpy as np
+    import torch
+    import fewbit_b200  # noqa: F401
+    for case in golden_ops:
+        if case['bf16']:
+            conv = lambda a: torch.from_numpy(a.view(np.int16).copy()).view(torch.bfloat16)  # noqa: E731
+            raw = lambda t: t.contiguous().view(torch.int16).numpy().view(np.uint16)  # noqa: E731
+        else:
+            conv = lambda a: torch.from_numpy(np.ascontiguousarray(a))  # noqa: E731
+            raw = lambda t: t.contiguous().numpy()  # noqa: E731
+        x, g, bounds, levels = (conv(case[k]) for k in ('x', 'g', 'bounds', 'levels'))
+        y, state = torch.ops.fewbit.quantize(x, bounds)
+        gin = torch.ops.fewbit.quantize_backward(g, state, levels)
+        assert np.array_equal(state.numpy(), case['state']), case['key']
+        assert np.array_equal(raw(gin).view(np.uint8), case['gin'].view(np.uint8)), case['key']
+        assert np.array_equal(raw(y).view(np.uint8), case['y'].view(np.uint8)), case['key']
+        if case['n'] > 1 and not case['bf16']:
+            leaf = x.clone().requires_grad_()
+            out = torch.ops.fewbit.gelu(leaf, bounds, levels)
+            out.backward(g)
+            assert np.array_equal(leaf.grad.numpy().view(np.uint8), case['gin'].view(np.uint8)), case['key']
