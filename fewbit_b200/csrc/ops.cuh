@@ -76,6 +76,15 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     return v;
 }
 
+#ifndef FEWBIT_ADDR_PAIRS
+#define FEWBIT_ADDR_PAIRS 1
+#endif
+__device__ __forceinline__ unsigned long long pack2(float v) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v));
+    return r;
+}
+
 template <typename T, int B> struct Bucketizer<T, B, false> {
     static constexpr int kSize = 1 << B;  // bounds padded with +inf to a power of two
     // Cells: enough to separate the borders of every shipped table, few enough that the
@@ -151,8 +160,27 @@ template <typename T, int B> struct Bucketizer<T, B, false> {
             for (int j = 0; j < 8; ++j) code[j] = exact(table, x[j]);
             return;
         }
+#if !FEWBIT_ADDR_PAIRS
 #pragma unroll
         for (int j = 0; j < 8; ++j) code[j] = lds_u8(entry_address(x[j]));
+#else
+        // entry_address() for two elements at a time: the clamp has no packed form, the
+        // denormal-range FMA does (see Pair below).
+        const unsigned long long cells2 = pack2(__uint_as_float((uint32_t)(kCells - 1)));
+        const unsigned long long base2 = pack2(lut_base);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            const float t0 = __saturatef(fmaf(x[j], scale, offset));
+            const float t1 = __saturatef(fmaf(x[j + 1], scale, offset));
+            unsigned long long t2, a2;
+            uint32_t a0, a1;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(t2) : "f"(t0), "f"(t1));
+            asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(a2) : "l"(t2), "l"(cells2), "l"(base2));
+            asm("mov.b64 {%0, %1}, %2;" : "=r"(a0), "=r"(a1) : "l"(a2));
+            code[j] = lds_u8(a0);
+            code[j + 1] = lds_u8(a1);
+        }
+#endif
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             if (lds_f32(table_base + 4 * code[j]) < x[j]) code[j] += 1;
@@ -187,32 +215,181 @@ __device__ __forceinline__ float lg2_approx(float v) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
 }
+// Packed fp32 pairs.  sm_100 has FFMA2: one issue slot, two fp32 FMAs on an aligned register pair
+// (same rounding as two FFMAs; |.| and negation fold into operand modifiers, equal halves into a
+// scalar-broadcast operand).  The transcendental kernels are bound by instruction issue, not by
+// the FMA pipe, so evaluating two elements per instruction is what buys time there.
+struct Pair {
+    unsigned long long bits;
+};
+__device__ __forceinline__ Pair pair(float lo, float hi) {
+    Pair r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.bits) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpair(Pair p, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p.bits));
+}
+
+// Lane-generic arithmetic: every bf16 formula below is written once over L = float (one element:
+// ragged kernel) or L = Pair (two elements per instruction: tile kernel).  Same operations in the
+// same order, so both give the same bits.  Multiply-adds are spelled out (fma_) rather than left
+// to contraction, for the same reason.
+template <class L> __device__ __forceinline__ L lane(float c);
+template <> __device__ __forceinline__ float lane<float>(float c) { return c; }
+template <> __device__ __forceinline__ Pair lane<Pair>(float c) { return pair(c, c); }
+
+__device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ Pair fma_(Pair a, Pair b, Pair c) {
+    Pair r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.bits) : "l"(a.bits), "l"(b.bits), "l"(c.bits));
+    return r;
+}
+__device__ __forceinline__ Pair mul_(Pair a, Pair b) {
+    Pair r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.bits) : "l"(a.bits), "l"(b.bits));
+    return r;
+}
+__device__ __forceinline__ Pair add_(Pair a, Pair b) {
+    Pair r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.bits) : "l"(a.bits), "l"(b.bits));
+    return r;
+}
+// Per-half operations of a Pair (MUFU, sign games, comparisons have no packed form).
+#define FEWBIT_HALVES_1(NAME, EXPR)                         \
+    __device__ __forceinline__ Pair NAME(Pair a) {          \
+        float v, w;                                         \
+        unpair(a, v, w);                                    \
+        float lo, hi;                                       \
+        { const float x = v; lo = (EXPR); }                 \
+        { const float x = w; hi = (EXPR); }                 \
+        return pair(lo, hi);                                \
+    }                                                       \
+    __device__ __forceinline__ float NAME(float x) { return (EXPR); }
+FEWBIT_HALVES_1(rcp_, rcp_approx(x))
+FEWBIT_HALVES_1(ex2_, ex2_approx(x))
+FEWBIT_HALVES_1(lg2_, lg2_approx(x))
+FEWBIT_HALVES_1(abs_, fabsf(x))
+FEWBIT_HALVES_1(neg_, -x)
+#undef FEWBIT_HALVES_1
+__device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ float copysign_(float mag, float sgn) { return copysignf(mag, sgn); }
+// a < b ? t : f   and   a > b ? t : f
+__device__ __forceinline__ float if_less(float a, float b, float t, float f) { return a < b ? t : f; }
+__device__ __forceinline__ float if_greater(float a, float b, float t, float f) { return a > b ? t : f; }
+__device__ __forceinline__ Pair min_(Pair a, Pair b) {
+    float a0, a1, b0, b1;
+    unpair(a, a0, a1), unpair(b, b0, b1);
+    return pair(fminf(a0, b0), fminf(a1, b1));
+}
+__device__ __forceinline__ Pair copysign_(Pair mag, Pair sgn) {
+    float m0, m1, s0, s1;
+    unpair(mag, m0, m1), unpair(sgn, s0, s1);
+    return pair(copysignf(m0, s0), copysignf(m1, s1));
+}
+__device__ __forceinline__ Pair if_less(Pair a, Pair b, Pair t, Pair f) {
+    float a0, a1, b0, b1, t0, t1, f0, f1;
+    unpair(a, a0, a1), unpair(b, b0, b1), unpair(t, t0, t1), unpair(f, f0, f1);
+    return pair(a0 < b0 ? t0 : f0, a1 < b1 ? t1 : f1);
+}
+__device__ __forceinline__ Pair if_greater(Pair a, Pair b, Pair t, Pair f) {
+    float a0, a1, b0, b1, t0, t1, f0, f1;
+    unpair(a, a0, a1), unpair(b, b0, b1), unpair(t, t0, t1), unpair(f, f0, f1);
+    return pair(a0 > b0 ? t0 : f0, a1 > b1 ? t1 : f1);
+}
+
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
-__device__ __forceinline__ float fast_exp(float x) { return ex2_approx(x * kLog2e); }
+namespace fast {   // the bf16 formulas (see the accuracy note above); L = float or Pair
+template <class L> __device__ __forceinline__ L exp(L x) { return ex2_(mul_(x, lane<L>(kLog2e))); }
+template <class L> __device__ __forceinline__ L exp_neg(L x) { return ex2_(mul_(x, lane<L>(-kLog2e))); }
 // log(1 + e^z): for z < -8 the sum 1 + e^z loses e^z's digits, and log1p(e^z) = e^z (1 - e^z/2 ..)
-__device__ __forceinline__ float fast_log1p_exp(float z) {
-    const float e = fast_exp(z);
-    return z < -8.0f ? e : kLn2 * lg2_approx(1.0f + e);
+template <class L> __device__ __forceinline__ L log1p_exp(L z) {
+    const L e = exp(z);
+    return if_less(z, lane<L>(-8.0f), e, mul_(lg2_(add_(e, lane<L>(1.0f))), lane<L>(kLn2)));
 }
 // e^z - 1 without cancellation near zero (|z| < 2^-9: z + z^2/2).
-__device__ __forceinline__ float fast_expm1(float z) {
-    return fabsf(z) < 0.001953125f ? fmaf(0.5f * z, z, z) : fast_exp(z) - 1.0f;
+template <class L> __device__ __forceinline__ L expm1(L z) {
+    return if_less(abs_(z), lane<L>(0.001953125f), fma_(mul_(z, lane<L>(0.5f)), z, z),
+                   add_(exp(z), lane<L>(-1.0f)));
 }
-// tanh: odd polynomial below 1/4 (relative error 3e-7), 1 - 2/(1 + e^{2|x|}) above.
-__device__ __forceinline__ float fast_tanh(float x) {
-    const float a = fabsf(x), x2 = x * x;
-    const float small = x * fmaf(x2, fmaf(x2, fmaf(x2, -0.05396825397f, 0.13333333333f), -0.33333333333f), 1.0f);
-    const float big = copysignf(fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(a * (2.0f * kLog2e))), 1.0f), x);
-    return a < 0.25f ? small : big;
+// tanh away from zero: sign(x) (1 - 2/(1 + e^{2|x|}))
+template <class L> __device__ __forceinline__ L tanh_big(L x) {
+    const L e = ex2_(mul_(abs_(x), lane<L>(2.0f * kLog2e)));
+    return copysign_(fma_(rcp_(add_(e, lane<L>(1.0f))), lane<L>(-2.0f), lane<L>(1.0f)), x);
 }
+// tanh: odd polynomial below 1/4 (relative error 3e-7), the form above elsewhere.
+template <class L> __device__ __forceinline__ L tanh(L x) {
+    const L x2 = mul_(x, x);
+    L p = fma_(x2, lane<L>(-0.05396825397f), lane<L>(0.13333333333f));
+    p = fma_(x2, p, lane<L>(-0.33333333333f));
+    p = fma_(x2, p, lane<L>(1.0f));
+    return if_less(abs_(x), lane<L>(0.25f), mul_(x, p), tanh_big(x));
+}
+// x - tanh(x) cancels below 1/4: the series x^3 (1/3 - 2 x^2/15 + 17 x^4/315) there.
+template <class L> __device__ __forceinline__ L tanhshrink(L x) {
+    const L x2 = mul_(x, x);
+    L p = fma_(x2, lane<L>(0.05396825397f), lane<L>(-0.13333333333f));
+    p = fma_(x2, p, lane<L>(0.33333333333f));
+    return if_less(abs_(x), lane<L>(0.25f), mul_(mul_(x, x2), p), add_(x, neg_(tanh_big(x))));
+}
+template <class L> __device__ __forceinline__ L sigmoid(L x) { return rcp_(add_(exp_neg(x), lane<L>(1.0f))); }
+template <class L> __device__ __forceinline__ L silu(L x) { return mul_(x, sigmoid(x)); }
+template <class L> __device__ __forceinline__ L softsign(L x) { return mul_(x, rcp_(add_(abs_(x), lane<L>(1.0f)))); }
+template <class L> __device__ __forceinline__ L logsigmoid(L x) {
+    return add_(min_(x, lane<L>(0.0f)), neg_(log1p_exp(neg_(abs_(x)))));
+}
+// tanh(log(1 + e)) = n / (n + 2) with n = e (e + 2), e = e^x (capped: 1 in fp32 beyond x = 20)
+template <class L> __device__ __forceinline__ L mish(L x) {
+    const L e = exp(min_(x, lane<L>(20.0f))), n = mul_(e, add_(e, lane<L>(2.0f)));
+    return mul_(mul_(x, n), rcp_(add_(n, lane<L>(2.0f))));
+}
+template <class L> __device__ __forceinline__ L softplus(L x, float beta, float threshold, float inv_beta) {
+    const L bx = mul_(x, lane<L>(beta));
+    return if_greater(bx, lane<L>(threshold), x, mul_(log1p_exp(bx), lane<L>(inv_beta)));
+}
+template <class L> __device__ __forceinline__ L elu(L x, float pos, float neg, float in_scale) {
+    return if_greater(x, lane<L>(0.0f), mul_(x, lane<L>(pos)),
+                      mul_(expm1(mul_(x, lane<L>(in_scale))), lane<L>(neg)));
+}
+// GELU through one branch-free erfc (derivation at GeluFn).
+template <class L> __device__ __forceinline__ L gelu(L x) {
+    const L one = lane<L>(1.0f);
+    const L s = rcp_(fma_(abs_(x), lane<L>(0.35355339059327376220f), one));
+    L p = fma_(lane<L>(2.816799879e-01f), s, lane<L>(-8.819190860e-01f));
+    p = fma_(p, s, lane<L>(5.309718251e-01f));
+    p = fma_(p, s, lane<L>(4.433360100e-01f));
+    p = fma_(p, s, lane<L>(1.451876998e+00f));
+    p = fma_(p, s, lane<L>(-1.825967312e+00f));
+    // erfc(t) = s * 2^(P(s) - log2(e) t^2),  log2(e) t^2 = (log2(e)/2) x^2
+    const L e = ex2_(fma_(mul_(x, lane<L>(-0.72134752044448170368f)), x, p));
+    // (x/2)(1 + erf(x/sqrt 2)) with erf = sign(x)(1 - erfc):  x/2 + |x/2| (1 - s e)
+    const L half = mul_(x, lane<L>(0.5f));
+    return fma_(abs_(half), fma_(neg_(s), e, one), half);
+}
+}  // namespace fast
+
+// A functor with a bf16 formula exposes it for one element and for a pair.
+// PAIRED says whether the tile kernel uses the pair form: measured per function on B200
+// (profiles/r01_function_sweep_3bit.md) -- it pays where the formula is mostly multiply-adds
+// (gelu +9 %, tanhshrink +9 %, tanh, mish, elu family) and not where it is mostly MUFU and selects.
+#define FEWBIT_BF16_FORMULA(PAIRED, CALL1, CALL2)                                              \
+    static constexpr bool kPaired = PAIRED;                                                    \
+    __device__ __forceinline__ float bf16_value(float x) const { return CALL1; }              \
+    __device__ __forceinline__ void bf16_pair(float &x0, float &x1) const {                    \
+        const Pair x = pair(x0, x1);                                                           \
+        unpair(CALL2, x0, x1);                                                                 \
+    }
 
 struct EluFamily {  // celu / elu / selu:  x > 0 ? x*pos : expm1(x*in_scale)*neg
     float pos, neg, in_scale;
     template <typename T> __device__ __forceinline__ float eval(float x) const {
-        if constexpr (sizeof(T) == 2) return x > 0.0f ? x * pos : fast_expm1(x * in_scale) * neg;
+        if constexpr (sizeof(T) == 2) return bf16_value(x);
         return x > 0.0f ? x * pos : expm1f(x * in_scale) * neg;
     }
+    FEWBIT_BF16_FORMULA(true, fast::elu<float>(x, pos, neg, in_scale), fast::elu<Pair>(x, pos, neg, in_scale))
 };
 struct CeluFn : EluFamily {  // codec.cu:517-526
     __host__ CeluFn(double alpha, double) : EluFamily{1.0f, (float)alpha, (float)(1.0 / alpha)} {}
@@ -244,21 +421,10 @@ struct GeluFn {  // codec.cu:539-544 (x * normcdf(x))
             // on linspace(-5, 5, 101) -- then fails at 1.1e-6; see DESIGN.md.)
             return (x * 0.5f) * (1.0f + erff(x * 0.70710678118654752440f));
         } else {
-            // bf16: the result is rounded to 8 bits, so erfc may come from the short branch-free
-            // evaluation above.  s = 1 / (1 + t/2) with t = |x| / sqrt 2.
-            const float s = rcp_approx(fmaf(fabsf(x), 0.35355339059327376220f, 1.0f));
-            float p = fmaf(2.816799879e-01f, s, -8.819190860e-01f);
-            p = fmaf(p, s, 5.309718251e-01f);
-            p = fmaf(p, s, 4.433360100e-01f);
-            p = fmaf(p, s, 1.451876998e+00f);
-            p = fmaf(p, s, -1.825967312e+00f);
-            // erfc(t) = s * 2^(P(s) - log2(e) t^2),  log2(e) t^2 = (log2(e)/2) x^2
-            const float erfc_t = s * ex2_approx(fmaf(x * -0.72134752044448170368f, x, p));
-            // (x/2)(1 + erf(x/sqrt 2)) with erf = sign(x)(1 - erfc):  x/2 + |x/2| (1 - erfc)
-            const float half = x * 0.5f;
-            return fmaf(fabsf(half), 1.0f - erfc_t, half);
+            return bf16_value(x);   // rounded to 8 bits: the short branch-free erfc is enough
         }
     }
+    FEWBIT_BF16_FORMULA(true, fast::gelu<float>(x), fast::gelu<Pair>(x))
 };
 struct HardswishFn {  // codec.cu:546-564
     __host__ HardswishFn(double, double) {}
@@ -269,9 +435,10 @@ struct HardswishFn {  // codec.cu:546-564
 struct LogSigmoidFn {  // codec.cu:566-576
     __host__ LogSigmoidFn(double, double) {}
     template <typename T> __device__ __forceinline__ float eval(float x) const {
-        if constexpr (sizeof(T) == 2) return fminf(0.0f, x) - fast_log1p_exp(-fabsf(x));
+        if constexpr (sizeof(T) == 2) return bf16_value(x);
         return fminf(0.0f, x) - log1pf(expf(-fabsf(x)));
     }
+    FEWBIT_BF16_FORMULA(true, fast::logsigmoid<float>(x), fast::logsigmoid<Pair>(x))
 };
 struct MishFn {  // codec.cu:578-586
     // tanh(log(1 + e)) = ((1+e)^2 - 1) / ((1+e)^2 + 1) = n / (n + 2) with n = e (e + 2), e = e^x:
@@ -280,27 +447,27 @@ struct MishFn {  // codec.cu:578-586
     // n / (n + 2) is already 1 in fp32.
     __host__ MishFn(double, double) {}
     template <typename T> __device__ __forceinline__ float eval(float x) const {
-        if constexpr (sizeof(T) == 2) {
-            const float e = fast_exp(fminf(x, 20.0f)), n = e * (e + 2.0f);
-            return x * n * rcp_approx(n + 2.0f);
-        }
+        if constexpr (sizeof(T) == 2) return bf16_value(x);
         const float e = expf(fminf(x, 20.0f)), n = e * (e + 2.0f);
         return x * (n / (n + 2.0f));
     }
+    FEWBIT_BF16_FORMULA(true, fast::mish<float>(x), fast::mish<Pair>(x))
 };
 struct SigmoidFn {  // codec.cu:602-607
     __host__ SigmoidFn(double, double) {}
     template <typename T> __device__ __forceinline__ float eval(float x) const {
-        if constexpr (sizeof(T) == 2) return rcp_approx(1.0f + fast_exp(-x));
+        if constexpr (sizeof(T) == 2) return bf16_value(x);
         return 1.0f / (1.0f + expf(-x));
     }
+    FEWBIT_BF16_FORMULA(true, fast::sigmoid<float>(x), fast::sigmoid<Pair>(x))
 };
 struct SiluFn {  // codec.cu:609-614
     __host__ SiluFn(double, double) {}
     template <typename T> __device__ __forceinline__ float eval(float x) const {
-        if constexpr (sizeof(T) == 2) return x * rcp_approx(1.0f + fast_exp(-x));
+        if constexpr (sizeof(T) == 2) return bf16_value(x);
         return x / (1.0f + expf(-x));
     }
+    FEWBIT_BF16_FORMULA(true, fast::silu<float>(x), fast::silu<Pair>(x))
 };
 struct SoftplusFn {  // codec.cu:616-632
     float beta, threshold, inv_beta;
@@ -308,40 +475,46 @@ struct SoftplusFn {  // codec.cu:616-632
     __host__ SoftplusFn(double b, double t)
         : beta((float)b), threshold((float)t), inv_beta((float)(1.0 / b)), unit_beta((float)b == 1.0f) {}
     template <typename T> __device__ __forceinline__ float eval(float x) const {
+        if constexpr (sizeof(T) == 2) return bf16_value(x);
         const float bx = x * beta;
-        if constexpr (sizeof(T) == 2) return bx > threshold ? x : fast_log1p_exp(bx) * inv_beta;
         const float soft = log1pf(expf(bx));
         return bx > threshold ? x : (unit_beta ? soft : soft / beta);   // x / 1 is exact: skip it
     }
+    FEWBIT_BF16_FORMULA(false, fast::softplus<float>(x, beta, threshold, inv_beta),
+                        fast::softplus<Pair>(x, beta, threshold, inv_beta))
 };
 struct SoftsignFn {  // codec.cu:634-639
     __host__ SoftsignFn(double, double) {}
     template <typename T> __device__ __forceinline__ float eval(float x) const {
-        if constexpr (sizeof(T) == 2) return x * rcp_approx(1.0f + fabsf(x));
+        if constexpr (sizeof(T) == 2) return bf16_value(x);
         return x / (1.0f + fabsf(x));
     }
+    FEWBIT_BF16_FORMULA(false, fast::softsign<float>(x), fast::softsign<Pair>(x))
 };
 struct TanhFn {  // codec.cu:641-646
     __host__ TanhFn(double, double) {}
     template <typename T> __device__ __forceinline__ float eval(float x) const {
-        if constexpr (sizeof(T) == 2) return fast_tanh(x);
+        if constexpr (sizeof(T) == 2) return bf16_value(x);
         return tanhf(x);
     }
+    FEWBIT_BF16_FORMULA(true, fast::tanh<float>(x), fast::tanh<Pair>(x))
 };
 struct TanhshrinkFn {  // codec.cu:648-653
     __host__ TanhshrinkFn(double, double) {}
     template <typename T> __device__ __forceinline__ float eval(float x) const {
-        if constexpr (sizeof(T) == 2) {
-            // x - tanh(x) cancels below 1/4: use the series x^3 (1/3 - 2 x^2/15 + 17 x^4/315) there
-            const float x2 = x * x;
-            const float small = x * x2 * fmaf(x2, fmaf(x2, 0.05396825397f, -0.13333333333f), 0.33333333333f);
-            return fabsf(x) < 0.25f ? small : x - fast_tanh(x);
-        }
+        if constexpr (sizeof(T) == 2) return bf16_value(x);
         return x - tanhf(x);
     }
+    FEWBIT_BF16_FORMULA(true, fast::tanhshrink<float>(x), fast::tanhshrink<Pair>(x))
 };
 
 // Forward op of a continuous activation: y = fn(x), code = bucket(x), eight values at a time.
+#ifndef FEWBIT_PAIRS
+#define FEWBIT_PAIRS 1
+#endif
+template <class Fn, typename = void> struct has_pairs : std::false_type {};
+template <class Fn> struct has_pairs<Fn, std::enable_if_t<Fn::kPaired>> : std::true_type {};
+
 template <class Fn, typename T, int B> struct QuantizeOp {
     static constexpr int kBits = B;
     static constexpr bool kHeavy = true;  // transcendental math: see TileConfig in launch.cuh
@@ -351,8 +524,13 @@ template <class Fn, typename T, int B> struct QuantizeOp {
     __device__ __forceinline__ void prepare(Scratch &s) { bucket.prepare(s); }
     __device__ __forceinline__ void apply(float (&v)[8], uint32_t (&code)[8]) const {
         bucket.lookup(v, code);
+        if constexpr (sizeof(T) == 2 && has_pairs<Fn>::value && FEWBIT_PAIRS) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fn.template eval<T>(v[j]);
+            for (int j = 0; j < 8; j += 2) fn.bf16_pair(v[j], v[j + 1]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fn.template eval<T>(v[j]);
+        }
     }
 };
 
@@ -439,7 +617,11 @@ struct SoftshrinkFn {  // codec.cu:450-465
     __device__ __forceinline__ float operator()(float x, uint32_t &m) const {
         const bool neg = x < -lambd, pos = x > lambd;
         m = (neg || pos) ? 1u : 0u;
-        return neg ? x + lambd : (pos ? x - lambd : 0.0f);
+        // both shifts up front and two selects: left as nested ternaries the bf16 instantiation
+        // compiled to divergent branches (59 % of HBM speed instead of 85 %)
+        const float up = x + lambd, down = x - lambd;
+        const float r = pos ? down : 0.0f;
+        return neg ? up : r;
     }
 };
 struct ThresholdFn {  // codec.cu:470-484
