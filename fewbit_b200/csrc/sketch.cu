@@ -25,30 +25,42 @@
 // sketch row the 32 lanes of a warp hold 32 consecutive features.
 //
 // CTA = 16 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-15
-// generate S (the generation is the most expensive part: ~17 instructions and 2 MUFU ops per
-// normal, so it gets 14 of the 16 warps and several independent Philox chains per thread);
-// warps 4-7 then run the epilogue (tcgen05.ld -> scale -> global).  Three-stage mbarrier
-// pipeline: full_x (TMA bytes), full_s (generator warps), empty (tcgen05.commit).
+// generate S; all 16 warps run the epilogue (tcgen05.ld -> scale -> global).  Three-stage
+// mbarrier pipeline: full_x (TMA bytes), full_s (generator warps), empty (tcgen05.commit).
+// The TMA and MMA loops are walked by their whole warp with only the asynchronous instruction under
+// an elect.sync predicate: under `if (lane == 0)` the compiler wraps every UTCHMMA in a uniform-
+// register retry loop that costs ~150 cycles per MMA, twice the MMA itself (measured).
 // Grid = (ceil(P / BN), ceil(D / 384), split_k); split-K partials are reduced by a tiny kernel.
 //
-// Sharing operands inside a thread-block cluster (Cx, Cy, 1), Cx, Cy in {1, 2}:
-//  * along y (feature tiles): generating S costs about twice the MMA time, and CTAs that differ
-//    only in their feature tile need the very same S tile.  CTA ry generates rows
-//    [ry BN/Cy, (ry+1) BN/Cy) of each stage into its own shared memory and pushes that block to
+// Three ways for CTAs that need the same data to share it (chosen by plan()):
+//  * pair mode, the default for Gaussian S when D is a multiple of 768: a 2 x 1 cluster is a CTA
+//    pair in the tcgen05 sense (cta_group::2).  The two CTAs own the two 384-feature halves of a
+//    768-feature slab and generate HALF of every S tile each; one M = 256 MMA, issued by the
+//    leader, reads X^T from both shared memories and each half of S once for both.  S is thus
+//    generated once per slab instead of once per feature tile, nothing is copied, and the MMA's
+//    shared-memory traffic per SM drops by a third.  The leader's full_x counts the TMA bytes of
+//    both CTAs (the peer's TMA signals the leader's barrier, .cta_group::2 form); the peer's
+//    generators arrive on a local barrier and its idle warp 1 forwards that to the leader with a
+//    cluster-scope release (~0.5 us, off the generators' critical path).  Grid axes are swapped
+//    (feature tiles along x): the hardware pairs CTAs that are adjacent along x of the cluster.
+//  * along y (feature tiles) without cta_group::2, cluster (1, 2): CTA ry generates rows
+//    [ry BN/2, (ry+1) BN/2) of each stage into its own shared memory and pushes that block to
 //    its y-peer with cp.async.bulk.shared::cluster (async proxy; completes transaction bytes on
 //    the PEER's full_s barrier, so the tensor core sees the data without a generic-proxy
-//    hand-over).
-//  * along x (sketch-row tiles): CTAs that differ only in their row tile stream the very same X
-//    tiles, and re-reading X from L2 once per row tile is what bounds the kernel when S is cheap
-//    (Rademacher).  Each CTA loads every Cx-th TMA box and multicasts it to its x-peers.
+//    hand-over).  Used for Rademacher S at D = 768: that case is bound by the MMA pipeline, and
+//    the pair's extra signalling hop costs more than the halved S traffic saves.
+//  * along x (sketch-row tiles), cluster (2, 1) with TMA multicast of the X boxes: kept for A/B
+//    runs (FEWBIT_B200_SKETCH_CLUSTER), measured slower -- L2 is not the limiter.
 // A stage may be overwritten only when every CTA of the cluster has consumed it: tcgen05.commit
 // multicasts its arrival to the `empty` barrier of all CTAs of the cluster.
+// FEWBIT_B200_SKETCH_TRACE=1 prints one CTA's timeline per call (benchmarks/sketch_trace.py).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 
 #include "../../include/fewbit_b200.h"
@@ -117,14 +129,67 @@ __device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const CUtens
         "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
         : "memory");
 }
+// kPair selects the two-SM forms (cta_group::2): one MMA spans the CTA pair of a cluster, M = 256.
+template <bool kPair>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                           uint32_t idesc, uint32_t accumulate) {
+    if constexpr (kPair)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+// TMA load whose completion bytes are counted on the LEADER CTA's barrier (shared::cluster address).
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1,
+                                                 uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(leader_bar)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {   // possibly a peer's barrier
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquires peers' writes
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on both CTAs of the pair
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+}
+// One lane of a converged warp.  The TMA and MMA loops are run by their WHOLE warp with only the
+// asynchronous instruction itself under this predicate: inside an `if (lane == 0)` region the
+// compiler cannot prove the descriptors warp-uniform and wraps every UTCHMMA / UTMALDG in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY retry loop (~150 cycles per MMA, twice the MMA itself).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ uint32_t cluster_cta_x() {
     uint32_t r;
@@ -229,6 +294,27 @@ __device__ __forceinline__ uint4 normal_octet(const Philox &rng, uint32_t o, uin
     const uint4 r = rng(make_uint4(o, p, off_lo, off_hi));
     return make_uint4(normal_pair(r.x), normal_pair(r.y), normal_pair(r.z), normal_pair(r.w));
 }
+// Two octets at once: the two Philox chains and the eight Box-Muller evaluations are independent,
+// and written as one straight-line block the scheduler interleaves them (a generator thread is
+// otherwise latency-bound: ~10 dependent multiply-xor rounds, then lg2 -> sqrt).
+__device__ __forceinline__ void normal_octet2(const Philox &rng, uint32_t o0, uint32_t p0, uint32_t o1, uint32_t p1,
+                                              uint32_t off_lo, uint32_t off_hi, uint4 &v0, uint4 &v1) {
+    uint4 c0 = make_uint4(o0, p0, off_lo, off_hi), c1 = make_uint4(o1, p1, off_lo, off_hi);
+    uint32_t a = rng.k0, b = rng.k1;
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        const uint32_t h00 = __umulhi(0xD2511F53u, c0.x), l00 = 0xD2511F53u * c0.x;
+        const uint32_t h10 = __umulhi(0xD2511F53u, c1.x), l10 = 0xD2511F53u * c1.x;
+        const uint32_t h01 = __umulhi(0xCD9E8D57u, c0.z), l01 = 0xCD9E8D57u * c0.z;
+        const uint32_t h11 = __umulhi(0xCD9E8D57u, c1.z), l11 = 0xCD9E8D57u * c1.z;
+        c0 = make_uint4(h01 ^ c0.y ^ a, l01, h00 ^ c0.w ^ b, l00);
+        c1 = make_uint4(h11 ^ c1.y ^ a, l11, h10 ^ c1.w ^ b, l10);
+        a += 0x9E3779B9u;
+        b += 0xBB67AE85u;
+    }
+    v0 = make_uint4(normal_pair(c0.x), normal_pair(c0.y), normal_pair(c0.z), normal_pair(c0.w));
+    v1 = make_uint4(normal_pair(c1.x), normal_pair(c1.y), normal_pair(c1.z), normal_pair(c1.w));
+}
 // kind 1: 128 signs S[p][128c .. 128c+127]; bit b of word w is entry 32w + b.
 __device__ __forceinline__ uint4 sign_block(const Philox &rng, uint32_t c, uint32_t p, uint32_t off_lo,
                                             uint32_t off_hi) {
@@ -240,6 +326,12 @@ __device__ __forceinline__ uint32_t sign_pair(uint32_t bits) {
 }
 
 // --------------------------------------------------------------------------- kernel ----
+
+__device__ __forceinline__ unsigned long long now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 struct Params {
     float *out;          // [P, D] (split_k == 1) or partials [split_k, P, D]
@@ -254,10 +346,12 @@ struct Params {
     int kind;
     int cluster_x;       // CTAs along grid.x that share X tiles (TMA multicast)
     int cluster_y;       // CTAs along grid.y that share one generated S tile
+    unsigned long long *trace;   // FEWBIT_B200_SKETCH_TRACE: per-role time stamps of CTA (0,0,0), else null
     int debug;           // timing experiments only (results are garbage): 1 = skip generating S,
-                         // 2 = skip loading X, 4 = skip issuing MMAs
+                         // 2 = skip loading X, 4 = skip issuing MMAs, 16 = declare A K-major
 };
 
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     extern __shared__ uint8_t smem_raw[];
@@ -267,8 +361,11 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * kStages + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p0 = blockIdx.x * prm.block_rows;
-    const int d0 = blockIdx.y * kFeaturesPerCta;
+    const bool traced = prm.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    if (traced && threadIdx.x == 0) prm.trace[0] = now_ns();
+    // Pair mode swaps the grid axes: a CTA pair must be adjacent along x of the cluster (2 x 1).
+    const int p0 = (kPair ? blockIdx.y : blockIdx.x) * prm.block_rows;
+    const int d0 = (kPair ? blockIdx.x : blockIdx.y) * kFeaturesPerCta;
     const int bn = prm.block_rows;
     const int nblocks = min(3, (prm.features - d0 + 127) / 128);   // 128-feature MMA blocks
     const int nboxes = min(6, (prm.features - d0 + 63) / 64);
@@ -285,104 +382,184 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     auto s_stage = [&](int s) { return smem_addr(smem + s * kStageBytes + kXStageBytes); };
 
     const int cx = prm.cluster_x, cy = prm.cluster_y, cluster = cx * cy;
-    const uint32_t rx = cx > 1 ? cluster_cta_x() : 0, ry = cy > 1 ? cluster_cta_y() : 0;   // rank = rx + ry * cx
+    const uint32_t rx = !kPair && cx > 1 ? cluster_cta_x() : 0;                           // rank = rx + ry * cx
+    const uint32_t ry = kPair ? cluster_cta_x() : (cy > 1 ? cluster_cta_y() : 0);           // which share of S is mine
     const int my_rows = bn / cy;                            // rows of each S tile this CTA generates
+    // Pair mode (cluster 1 x 2, cta_group::2): the two CTAs own the two 384-feature halves of a
+    // 768-feature slab and HALF of every S tile each; one M = 256 MMA, issued by the leader (ry = 0),
+    // reads X^T from both shared memories and each half of S once for both.  The leader's full_x
+    // counts the TMA bytes of both CTAs, its full_s the generator warps of both.
+    const bool leader = !kPair || ry == 0;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full_x(s), 1);
-            mbar_init(full_s(s), kGeneratorWarps + (cy > 1 ? 1 : 0));   // + the expect_tx arrival
-            mbar_init(empty(s), cluster);                               // one commit per CTA
+            // own generator warps, + the peer's forwarded arrival (pair leader) or the expect_tx arrival (cy > 1)
+            mbar_init(full_s(s), kGeneratorWarps + ((kPair ? ry == 0 : cy > 1) ? 1 : 0));
+            mbar_init(empty(s), kPair ? 1 : cluster);                   // one commit per issuing CTA
         }
         mbar_init(accum_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM allocation is warp-wide; the same warp frees it
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_addr(tmem_slot)),
-                     "r"(kTmemColumns));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    if (warp == 1) {  // TMEM allocation is warp-wide; the same warp frees it (one warp per CTA, also in pair mode)
+        if constexpr (kPair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_addr(tmem_slot)),
+                         "r"(kTmemColumns));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_addr(tmem_slot)),
+                         "r"(kTmemColumns));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (cluster > 1) cluster_sync();          // peers' barriers exist before anyone signals them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (traced && threadIdx.x == 0) prm.trace[1] = now_ns();
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer ----
-        if (lane == 0) {
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % kStages;
-                mbar_wait(empty(s), ((it / kStages) & 1) ^ 1);
-                if (prm.debug & 2) { mbar_arrive(full_x(s)); continue; }
-                mbar_expect_tx(full_x(s), nboxes * kBoxBytes);                         // all boxes, whoever loads them
-                if (cy > 1) mbar_expect_tx(full_s(s), (cy - 1) * my_rows * 128);       // the y-peer's block
-                const int token = (int)((kb_begin + it) * kBlockK);
-                if (cx > 1) {
-                    const uint16_t mask = (uint16_t)(((1u << cx) - 1u) << (ry * cx));  // my row of the cluster
-                    for (int b = (int)rx; b < nboxes; b += cx)
-                        tma_load_2d_multicast(x_stage(s) + b * kBoxBytes, &x_map, d0 + 64 * b, token, full_x(s), mask);
-                } else {
+        for (int it = 0; it < iters; ++it) {
+            const int s = it % kStages;
+            mbar_wait(empty(s), ((it / kStages) & 1) ^ 1);
+            const int token = (int)((kb_begin + it) * kBlockK);
+            if (elect_one()) {
+                if (prm.debug & 2) {
+                    if (leader) mbar_arrive(full_x(s));
+                } else if constexpr (kPair) {
+                    if (leader) mbar_expect_tx(full_x(s), 2 * nboxes * kBoxBytes);     // both CTAs' boxes
+                    const uint32_t bar = map_to_cta(full_x(s), 0);
                     for (int b = 0; b < nboxes; ++b)
-                        tma_load_2d(x_stage(s) + b * kBoxBytes, &x_map, d0 + 64 * b, token, full_x(s));
+                        tma_load_2d_pair(x_stage(s) + b * kBoxBytes, &x_map, d0 + 64 * b, token, bar);
+                } else {
+                    mbar_expect_tx(full_x(s), nboxes * kBoxBytes);                     // all boxes, whoever loads them
+                    if (cy > 1) mbar_expect_tx(full_s(s), (cy - 1) * my_rows * 128);   // the y-peer's block
+                    if (cx > 1) {
+                        const uint16_t mask = (uint16_t)(((1u << cx) - 1u) << (ry * cx));  // my row of the cluster
+                        for (int b = (int)rx; b < nboxes; b += cx)
+                            tma_load_2d_multicast(x_stage(s) + b * kBoxBytes, &x_map, d0 + 64 * b, token, full_x(s), mask);
+                    } else {
+                        for (int b = 0; b < nboxes; ++b)
+                            tma_load_2d(x_stage(s) + b * kBoxBytes, &x_map, d0 + 64 * b, token, full_x(s));
+                    }
                 }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         // -------------------------------------------------------------- MMA issuer ----
-        if (lane == 0) {
-            // cute::UMMA::InstrDescriptor: D = f32, A = B = bf16, A MN-major, B K-major, N, M = 128.
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (0u << 16) |
-                                   ((uint32_t)(bn >> 3) << 17) | ((128u >> 4) << 24);
+        if (leader) {   // the whole warp walks the pipeline; one elected lane issues (see elect_one)
+            // cute::UMMA::InstrDescriptor: D = f32, A = B = bf16, A MN-major, B K-major, N, M = 128
+            // per CTA (256 across the pair).
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((prm.debug & 16) ? 0u : (1u << 15)) | (0u << 16) |
+                                   ((uint32_t)(bn >> 3) << 17) | (((kPair ? 256u : 128u) >> 4) << 24);
+            // Shared-memory descriptors differ only in the 14-bit address field of their low word:
+            //   A: 64-feature groups 8192 B apart (LBO), 8-token groups 1024 B apart (SBO); +2048 B per
+            //      16 tokens; 128 features = two boxes.
+            //   B: rows of 128 B (64 tokens), 8-row groups 1024 B apart (SBO); +32 B per 16 tokens.
+            const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t a_lo = ((x_stage(0) & 0x3FFFFu) >> 4) | ((uint32_t)(kBoxBytes >> 4) << 16);
+            const uint32_t b_lo = ((s_stage(0) & 0x3FFFFu) >> 4) | ((16u >> 4) << 16);
+            const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const bool skip_mma = (prm.debug & 4) != 0;
+            unsigned long long wait_x = 0, wait_s = 0;
             for (int it = 0; it < iters; ++it) {
                 const int s = it % kStages;
                 const uint32_t parity = (it / kStages) & 1;
+                const unsigned long long w0 = traced ? now_ns() : 0;
                 mbar_wait(full_x(s), parity);
-                mbar_wait(full_s(s), parity);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                for (int k = 0; k < ((prm.debug & 4) ? 0 : kBlockK / 16); ++k) {
-                    // B: rows of 128 B (64 tokens), 8-row groups 1024 B apart; +32 B per 16 tokens.
-                    const uint64_t desc_b = smem_desc(s_stage(s) + 32 * k, 16, 1024);
-                    for (int m = 0; m < nblocks; ++m) {
-                        // A: 64-feature groups 8192 B apart (LBO), 8-token groups 1024 B apart
-                        // (SBO); +2048 B per 16 tokens; 128 features = two boxes.
-                        const uint64_t desc_a = smem_desc(x_stage(s) + m * 2 * kBoxBytes + 2048 * k, kBoxBytes, 1024);
-                        umma_bf16(tmem_base + m * kMaxRows, desc_a, desc_b, idesc, (it | k) != 0);
-                    }
+                const unsigned long long w1 = traced ? now_ns() : 0;
+                if constexpr (kPair) mbar_wait_cluster(full_s(s), parity);   // the peer's generators wrote its half
+                else mbar_wait(full_s(s), parity);
+                if (traced && lane == 0) {
+                    const unsigned long long w2 = now_ns();
+                    wait_x += w1 - w0, wait_s += w2 - w1;
+                    if (it == 0) prm.trace[2] = w2;
                 }
-                // smem slot reusable once these MMAs have read it -- in every CTA of the cluster
-                if (cluster > 1) umma_commit_cluster(empty(s), (uint16_t)((1u << cluster) - 1));
-                else umma_commit(empty(s));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint32_t stage_off = (uint32_t)s * (uint32_t)(kStageBytes >> 4);
+                    if (!skip_mma) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            const uint64_t desc_b = ((uint64_t)desc_hi << 32) | (b_lo + stage_off + 2u * k);
+#pragma unroll
+                            for (int m = 0; m < 3; ++m) {
+                                if (m < nblocks) {
+                                    const uint64_t desc_a = ((uint64_t)desc_hi << 32) |
+                                                            (a_lo + stage_off + (uint32_t)((m * 2 * kBoxBytes + 2048 * k) >> 4));
+                                    umma_bf16<kPair>(tmem + m * kMaxRows, desc_a, desc_b, idesc, (it | k) != 0);
+                                }
+                            }
+                        }
+                    }
+                    // smem slot reusable once these MMAs have read it -- in every CTA of the cluster
+                    if constexpr (kPair) umma_commit_pair(empty(s));
+                    else if (cluster > 1) umma_commit_cluster(empty(s), (uint16_t)((1u << cluster) - 1));
+                    else umma_commit(empty(s));
+                }
+                __syncwarp();
             }
-            umma_commit(accum_full);          // accumulators complete
+            if (elect_one()) {   // accumulators complete (in both CTAs of a pair)
+                if constexpr (kPair) umma_commit_pair(accum_full);
+                else umma_commit(accum_full);
+            }
+            __syncwarp();
+            if (traced && lane == 0) prm.trace[3] = now_ns(), prm.trace[6] = wait_x, prm.trace[7] = wait_s;
+        } else {
+            // Pair mode, second CTA: forward "my half of S is written" to the leader's barrier.  The
+            // cluster-scope release costs ~0.5 us; paid here, on an otherwise idle warp, it stays off
+            // the generators' critical path.
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % kStages;
+                mbar_wait(full_s(s), (it / kStages) & 1);
+                if (elect_one()) mbar_arrive_cluster(map_to_cta(full_s(s), 0));
+                __syncwarp();
+            }
         }
     } else {
         // -------------------------------------------------------------- generators ----
         const Philox rng{prm.seed_lo, prm.seed_hi};
         const int gt = threadIdx.x - 64;                       // 0 .. 447
+        unsigned long long wait_e = 0, busy = 0;
+        long long ph[4] = {0, 0, 0, 0};      // cycles: generate + store, proxy fence, block sync + push, arrive
         for (int it = 0; it < iters; ++it) {
             const int s = it % kStages;
+            const unsigned long long w0 = traced && gt == 0 ? now_ns() : 0;
             mbar_wait(empty(s), ((it / kStages) & 1) ^ 1);
+            const unsigned long long g0 = traced && gt == 0 ? now_ns() : 0;
+            const long long c0 = traced && gt == 0 ? clock64() : 0;
+            if (traced && gt == 0) wait_e += g0 - w0;
             uint8_t *tile = smem + s * kStageBytes + kXStageBytes;
             const int64_t kb = kb_begin + it;
             const int row0 = (int)ry * my_rows;                // this CTA's block of the tile
+            const int place = kPair ? row0 : 0;                // pair mode: the block sits at the tile start
             if (prm.debug & 1) {
             } else if (prm.kind == 0) {
                 // One Philox call = 8 normals = one 16-byte chunk of a 128-byte K-major row.
                 // K-major SW128: chunk index XOR (row mod 8).  Up to 3 chunks per thread
                 // (160 rows x 8 chunks over 448 threads), independent chains interleave.
                 const int chunks = my_rows * 8;
-#pragma unroll
-                for (int j = 0; j < (kMaxRows * 8 + kGeneratorThreads - 1) / kGeneratorThreads; ++j) {
-                    const int i = gt + j * kGeneratorThreads;
-                    if (i < chunks) {
-                        const int row = row0 + (i >> 3), o = i & 7;
-                        const uint4 v = normal_octet(rng, (uint32_t)(kb * 8 + o), (uint32_t)(p0 + row),
-                                                     prm.off_lo, prm.off_hi);
-                        *reinterpret_cast<uint4 *>(tile + (row >> 3) * 1024 + (row & 7) * 128 + ((o ^ (row & 7)) << 4)) = v;
-                    }
+                auto put = [&](int i, const uint4 &v) {
+                    const int r = row0 - place + (i >> 3), o = i & 7;
+                    *reinterpret_cast<uint4 *>(tile + (r >> 3) * 1024 + (r & 7) * 128 + ((o ^ (r & 7)) << 4)) = v;
+                };
+                // chunks i and i + G together while both exist (two interleaved chains), then at most one
+                int i = gt;
+                for (; i + kGeneratorThreads < chunks; i += 2 * kGeneratorThreads) {
+                    const int i1 = i + kGeneratorThreads;
+                    uint4 v0, v1;
+                    normal_octet2(rng, (uint32_t)(kb * 8 + (i & 7)), (uint32_t)(p0 + row0 + (i >> 3)),
+                                  (uint32_t)(kb * 8 + (i1 & 7)), (uint32_t)(p0 + row0 + (i1 >> 3)), prm.off_lo,
+                                  prm.off_hi, v0, v1);
+                    put(i, v0), put(i1, v1);
                 }
+                if (i < chunks)
+                    put(i, normal_octet(rng, (uint32_t)(kb * 8 + (i & 7)), (uint32_t)(p0 + row0 + (i >> 3)), prm.off_lo,
+                                        prm.off_hi));
             } else {
                 // One Philox call = 128 signs; a 64-token stage uses half of it (two words), and
                 // each task expands one word = 32 tokens = four 16-byte chunks of a row, so that
@@ -392,18 +569,21 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
                     const int row = row0 + (task >> 1), half = task & 1;
                     const uint4 w = sign_block(rng, (uint32_t)(kb >> 1), (uint32_t)(p0 + row), prm.off_lo, prm.off_hi);
                     const uint32_t word = (kb & 1) ? (half ? w.w : w.z) : (half ? w.y : w.x);
-                    uint8_t *base = tile + (row >> 3) * 1024 + (row & 7) * 128;
+                    const int r = row - place;
+                    uint8_t *base = tile + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const uint32_t bits = word >> (c * 8);
                         const int o = half * 4 + c;
-                        *reinterpret_cast<uint4 *>(base + ((o ^ (row & 7)) << 4)) =
+                        *reinterpret_cast<uint4 *>(base + ((o ^ (r & 7)) << 4)) =
                             make_uint4(sign_pair(bits), sign_pair(bits >> 2), sign_pair(bits >> 4), sign_pair(bits >> 6));
                     }
                 }
             }
+            const long long c1 = traced && gt == 0 ? clock64() : 0;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
-            if (cy > 1) {
+            const long long c2 = traced && gt == 0 ? clock64() : 0;
+            if (!kPair && cy > 1) {
                 // all generator threads have written (and fenced) this CTA's block: push it to the y-peers
                 asm volatile("bar.sync 1, %0;" ::"n"(kGeneratorThreads) : "memory");
                 if (gt == 0) {
@@ -415,41 +595,56 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(full_s(s));
+            const long long c3 = traced && gt == 0 ? clock64() : 0;
+            if (traced && gt == 0) ph[0] += c1 - c0, ph[1] += c2 - c1, ph[2] += c3 - c2;
+            if (traced && gt == 0) busy += now_ns() - g0;
+            if (lane == 0) mbar_arrive(full_s(s));       // pair mode, second CTA: warp 1 forwards it
+            if (traced && gt == 0) ph[3] += clock64() - c3;
         }
-        // ---------------------------------------------------------------- epilogue ----
-        if (warp >= 4 && warp < 8) {
-            mbar_wait(accum_full, 0);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int quarter = warp & 3;                       // TMEM lanes [32q, 32q + 32)
-            float *out = prm.out + (prm.split_k > 1 ? (int64_t)blockIdx.z * prm.rows * prm.features : 0);
-            const float scale = prm.split_k > 1 ? 1.0f : prm.scale;
-            for (int m = 0; m < nblocks; ++m) {
-                const int d = d0 + m * 128 + quarter * 32 + lane;
-                for (int c = 0; c < bn; c += 16) {
-                    uint32_t v[16];
-                    tmem_load16(tmem_base + ((uint32_t)(quarter * 32) << 16) + m * kMaxRows + c, v);
-                    if (iters == 0) {
+        if (traced && gt == 0) prm.trace[8] = wait_e, prm.trace[9] = now_ns(), prm.trace[10] = busy;
+        if (traced && gt == 0)
+            for (int j = 0; j < 4; ++j) prm.trace[11 + j] = (unsigned long long)(ph[j] / max(iters, 1));
+    }
+    // -------------------------------------------------------------------- epilogue ----
+    // All 16 warps: a warp reads the TMEM lanes of its quadrant (warp % 4); the four warps of a
+    // quadrant share its (feature block, 16-column) units.  For a fixed sketch row the 32 lanes
+    // hold 32 consecutive features: every store instruction writes one 128-byte line.
+    {
+        mbar_wait(accum_full, 0);
+        if (traced && warp == 4 && lane == 0) prm.trace[4] = now_ns();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int quarter = warp & 3;                       // TMEM lanes [32q, 32q + 32)
+        float *out = prm.out + (prm.split_k > 1 ? (int64_t)blockIdx.z * prm.rows * prm.features : 0);
+        const float scale = prm.split_k > 1 ? 1.0f : prm.scale;
+        const int units_per_block = bn / 16;
+        for (int u = warp >> 2; u < nblocks * units_per_block; u += kThreads / 128) {
+            const int m = u / units_per_block, c = (u % units_per_block) * 16;
+            const int d = d0 + m * 128 + quarter * 32 + lane;
+            uint32_t v[16];
+            tmem_load16(tmem_base + ((uint32_t)(quarter * 32) << 16) + m * kMaxRows + c, v);
+            if (iters == 0) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = 0;
-                    }
-                    if (d < prm.features) {
+                for (int j = 0; j < 16; ++j) v[j] = 0;
+            }
+            if (d < prm.features) {
+                float *dst = out + (int64_t)(p0 + c) * prm.features + d;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int p = p0 + c + j;
-                            if (p < prm.rows) out[(int64_t)p * prm.features + d] = __uint_as_float(v[j]) * scale;
-                        }
-                    }
-                }
+                for (int j = 0; j < 16; ++j)
+                    if (p0 + c + j < prm.rows) dst[(int64_t)j * prm.features] = __uint_as_float(v[j]) * scale;
             }
         }
     }
+    if (traced && warp == 4 && lane == 0) prm.trace[5] = now_ns();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (cluster > 1) cluster_sync();          // nobody leaves while peers may still signal it
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"(kTmemColumns));
+        if constexpr (kPair)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                         "r"(kTmemColumns));
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                         "r"(kTmemColumns));
     }
 }
 
@@ -510,31 +705,51 @@ static EncodeTiled encode_tiled() {
 // waves * (time of one CTA).  Measured on B200 (profiles/r01_sketch_kernel.md): clusters of 8
 // along y lose to independent CTAs at D = 3072 (8-CTA placement leaves SMs idle and the lock-step
 // `empty` barrier couples eight pipelines), so both axes are capped at 2.
-static void plan(int rows, int features, int64_t tokens, int sms, int &bn, int &split_k, int &cx, int &cy) {
+static void plan(int rows, int features, int64_t tokens, int kind, int sms, int &bn, int &split_k, int &cx,
+                 int &cy, bool &pair) {
     const int dtiles = (features + kFeaturesPerCta - 1) / kFeaturesPerCta;
     const int64_t kblocks = std::max<int64_t>(1, (tokens + kBlockK - 1) / kBlockK);
     // Default from the A/B runs in profiles/r01_sketch_kernel.md: S sharing between the two feature
     // tiles of D = 768 helps (133 -> 123 us); X multicast does not (159 us), L2 is not the limiter.
     cy = dtiles == 2 ? 2 : 1;
     cx = 1;
+    // Pair mode (cta_group::2 MMAs over a 1 x 2 cluster) whenever the feature tiles come in full
+    // pairs: each S tile is generated once per pair and read from shared memory once per pair.
+    // Measured (profiles/r01_sketch_kernel.md): with Gaussian entries the kernel is bound by generating
+    // S and the pair halves that work (D = 3072: 493 -> 406 us); with Rademacher entries it is bound by
+    // the MMA pipeline, and the extra hop of the peer's "S ready" signal costs more than it saves.
+    pair = features % (2 * kFeaturesPerCta) == 0 && kind == 0;
+    if (const char *env = std::getenv("FEWBIT_B200_SKETCH_PAIR")) pair = pair && std::atoi(env) != 0;
+    if (pair) cy = 2;
     if (const char *env = std::getenv("FEWBIT_B200_SKETCH_CLUSTER")) {   // A/B runs: "<cx><cy>", e.g. 11, 21, 12, 22
         const int v = std::atoi(env);
         if (v / 10 >= 1 && v / 10 <= 2) cx = rows > 160 ? v / 10 : 1;
         if (v % 10 >= 1 && v % 10 <= 2) cy = std::min(cy, v % 10);
+        pair = false;
     }
     double best = 1e300;
     bn = 64, split_k = 1;
+    int only_bn = 0, only_sk = 0;
+    if (const char *env = std::getenv("FEWBIT_B200_SKETCH_BN")) only_bn = std::atoi(env);   // tuning runs
+    if (const char *env = std::getenv("FEWBIT_B200_SKETCH_SPLITK")) only_sk = std::atoi(env);
     for (int cand = 160; cand >= 64; cand -= 16) {
         if ((cand / 8) % cy != 0) continue;
+        if (only_bn && cand != only_bn) continue;
         const int ptiles = ((rows + cand - 1) / cand + cx - 1) / cx * cx;
         for (int sk = 1; sk <= 8 && sk <= kblocks; ++sk) {
+            if (only_sk && sk != only_sk) continue;
             const int64_t ctas = (int64_t)ptiles * dtiles * sk;
             const int64_t waves = (ctas + sms - 1) / sms;
-            // per 64-token block: S generation ~11 cycles per generated row, MMA 6 cycles per row,
-            // and the 48 KB X tile needs ~1100 cycles to arrive from L2 (half with multicast)
-            const double block = std::max({cand * 11.0 / cy, cand * 6.0, 1100.0 / cx});
-            const double per_cta = (double)((kblocks + sk - 1) / sk) * block + 8000.0;
-            const double cost = (double)waves * per_cta * (1.0 + 0.01 * (sk - 1));
+            // Cycles, fitted to the (BN, split_k) sweep in profiles/r01_sketch_kernel.md.  Per 64-token
+            // stage: ~17 cycles per generated Gaussian row (the generators are latency-bound), never
+            // under ~1300 (pipeline round trip; 12 MMAs of ~90-107 cycles).  Per CTA: ~20000 for
+            // prologue + epilogue (the epilogue writes at HBM speed).  Split-K adds the partials'
+            // round trip through memory: 8 bytes per output element and split at ~5 TB/s.
+            const double generated = kind == 0 ? (double)cand / cy * 17.0 : 0.0;
+            const double block = std::max({generated, 1300.0, cand * 9.0});   // 12 MMAs: ~9 cycles per row
+            const double per_cta = (double)((kblocks + sk - 1) / sk) * block + 20000.0;
+            const double reduce = sk > 1 ? (double)sk * rows * features * 8.0 / 5e12 * 1.9e9 : 0.0;
+            const double cost = (double)waves * per_cta + reduce;
             if (cost < best) best = cost, bn = cand, split_k = sk;
         }
     }
@@ -550,8 +765,11 @@ extern "C" {
 
 size_t fewbit_sketch_workspace_bytes(int64_t tokens, int features, int rows) {
     int bn, split_k, cx, cy;
-    plan(rows, features, tokens, sm_count(), bn, split_k, cx, cy);
-    return split_k > 1 ? (size_t)split_k * rows * features * sizeof(float) : 0;
+    bool pair;
+    plan(rows, features, tokens, 0, sm_count(), bn, split_k, cx, cy, pair);
+    size_t bytes = split_k > 1 ? (size_t)split_k * rows * features * sizeof(float) : 0;
+    plan(rows, features, tokens, 1, sm_count(), bn, split_k, cx, cy, pair);   // the larger of the two kinds
+    return std::max(bytes, split_k > 1 ? (size_t)split_k * rows * features * sizeof(float) : (size_t)0);
 }
 
 int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t tokens, int features,
@@ -563,7 +781,8 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
     if (!encode) return (int)cudaErrorNotSupported;
     cudaStream_t s = (cudaStream_t)stream;
     int bn, split_k, cx, cy;
-    plan(rows, features, tokens, sm_count(), bn, split_k, cx, cy);
+    bool pair;
+    plan(rows, features, tokens, kind, sm_count(), bn, split_k, cx, cy, pair);
     if (split_k > 1 && !workspace) return FEWBIT_EINVAL;
 
     CUtensorMap map;
@@ -582,7 +801,15 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
     prm.kblocks_per_split = (int)((kblocks + split_k - 1) / split_k);
     prm.split_k = split_k, prm.scale = scale, prm.kind = kind, prm.cluster_x = cx, prm.cluster_y = cy;
     prm.debug = 0;
+    prm.trace = nullptr;
     if (const char *env = std::getenv("FEWBIT_B200_SKETCH_DEBUG")) prm.debug = std::atoi(env);
+    static unsigned long long *trace_buffer = nullptr;
+    const bool tracing = std::getenv("FEWBIT_B200_SKETCH_TRACE") != nullptr;
+    if (tracing) {
+        if (!trace_buffer) cudaMalloc(&trace_buffer, 16 * sizeof(unsigned long long));
+        cudaMemsetAsync(trace_buffer, 0, 16 * sizeof(unsigned long long), s);
+        prm.trace = trace_buffer;
+    }
     prm.seed_lo = (uint32_t)seed, prm.seed_hi = (uint32_t)(seed >> 32);
     prm.off_lo = (uint32_t)offset, prm.off_hi = (uint32_t)(offset >> 32);
 
@@ -591,23 +818,40 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
     int device = 0;
     if (cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= 64) device = 0;
     if (!configured[device]) {
-        cudaError_t e = cudaFuncSetAttribute(sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(sketch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(sketch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) return (int)e;
         configured[device] = true;
     }
     cudaLaunchConfig_t cfg{};
     // grid.x rounded up to whole clusters: surplus CTAs compute rows >= P, which are never stored
     cfg.gridDim = dim3(((rows + bn - 1) / bn + cx - 1) / cx * cx, (features + kFeaturesPerCta - 1) / kFeaturesPerCta, split_k);
+    if (pair) std::swap(cfg.gridDim.x, cfg.gridDim.y);      // feature tiles (the pairs) along x
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = kSmemBytes;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cx, attr[0].val.clusterDim.y = cy, attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = pair ? 2 : cx, attr[0].val.clusterDim.y = pair ? 1 : cy, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    cudaError_t launched = cudaLaunchKernelEx(&cfg, sketch_kernel, map, prm);
+    cudaError_t launched = pair ? cudaLaunchKernelEx(&cfg, sketch_kernel<true>, map, prm)
+                                : cudaLaunchKernelEx(&cfg, sketch_kernel<false>, map, prm);
     if (launched != cudaSuccess) return (int)launched;
     note_launch();
+    if (tracing) {   // diagnostics only: synchronises
+        unsigned long long t[16];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(t, trace_buffer, sizeof(t), cudaMemcpyDeviceToHost);
+        std::fprintf(stderr,
+                     "[sketch trace] D=%d bn=%d split_k=%d pair=%d grid=%ux%ux%u | setup %.1f us, first MMA +%.1f, "
+                     "MMA loop %.1f (waited X %.1f, S %.1f), generators done +%.1f (waited empty %.1f, generating %.1f), "
+                     "accumulators seen +%.1f, epilogue %.1f | generator thread 0, cycles per stage: generate %llu, proxy fence %llu, "
+                     "sync+push %llu, arrive %llu\n",
+                     features, bn, split_k, (int)pair, cfg.gridDim.x, cfg.gridDim.y, cfg.gridDim.z,
+                     (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3, t[6] * 1e-3, t[7] * 1e-3,
+                     (t[9] - t[1]) * 1e-3, t[8] * 1e-3, t[10] * 1e-3, (t[4] - t[1]) * 1e-3, (t[5] - t[4]) * 1e-3, t[11], t[12], t[13], t[14]);
+    }
     if (split_k > 1) {
         const int64_t count = (int64_t)rows * features;
         reduce_splits_kernel<<<(unsigned)std::min<int64_t>((count + 255) / 256, sm_count() * 8), 256, 0, s>>>(
