@@ -22,6 +22,9 @@
 #ifndef FEWBIT_U_HEAVY
 #define FEWBIT_U_HEAVY 4
 #endif
+#ifndef FEWBIT_MAX_CTAS_PER_SM
+#define FEWBIT_MAX_CTAS_PER_SM 4
+#endif
 #ifndef FEWBIT_MINB_LIGHT
 #define FEWBIT_MINB_LIGHT 1
 #endif
@@ -65,6 +68,11 @@ int sm_count();      // api.cu: SM count of the current device (cached per devic
 
 template <class Op, typename T> struct TileConfig {
     static constexpr bool kHeavy = Op::kHeavy;
+    // Resident CTAs per SM the persistent grid is sized for.  The light fp32 kernels fit five, but
+    // four (32 warps, 32 KB of loads in flight per SM) is measurably the better operating point
+    // of the memory system: backward 88 % -> 94-95 % of the HBM peak on a 200 MB tensor, forward
+    // 86 % -> 91-93 % (profiles/r01_function_sweep_3bit.md).  The bf16 kernels sit at four anyway.
+    static constexpr int kMaxCtasPerSm = FEWBIT_MAX_CTAS_PER_SM;
     static constexpr int kSubtiles =
         kHeavy ? FEWBIT_U_HEAVY : (sizeof(T) == 2 ? FEWBIT_U_LIGHT_BF16 : FEWBIT_U_LIGHT_F32);
     static constexpr int kMinBlocks =
@@ -73,7 +81,7 @@ template <class Op, typename T> struct TileConfig {
 
 // Resident CTAs per SM for `kernel` (occupancy API, cached per instantiation), overridable
 // with FEWBIT_B200_CTAS_PER_SM for tuning runs.
-template <auto kernel> int resident_ctas() {
+template <auto kernel> int resident_ctas(int most) {
     static int cached = 0;
     if (cached == 0) {
         int blocks = 1;
@@ -81,6 +89,7 @@ template <auto kernel> int resident_ctas() {
                 cudaSuccess ||
             blocks < 1)
             blocks = 1;
+        blocks = std::min(blocks, most);
         if (const char *env = std::getenv("FEWBIT_B200_CTAS_PER_SM")) {
             int v = std::atoi(env);
             if (v > 0) blocks = std::min(blocks, v);
@@ -105,7 +114,7 @@ cudaError_t launch_forward(const T *x, T *y, uint8_t *state, int64_t n, const Op
     if (ntiles > 0) {
         constexpr auto kernel = forward_tiles_kernel<Op, T, U, TileConfig<Op, T>::kMinBlocks>;
         const int64_t want = (ntiles + kWarps - 1) / kWarps;
-        const int64_t cap = (int64_t)sm_count() * resident_ctas<kernel>();
+        const int64_t cap = (int64_t)sm_count() * resident_ctas<kernel>(TileConfig<Op, T>::kMaxCtasPerSm);
         kernel<<<(unsigned)std::min(want, cap), kThreads, 0, stream>>>(x, y, state, ntiles, op);
         note_launch();
     }
@@ -131,7 +140,7 @@ cudaError_t launch_backward(const uint8_t *state, const T *gout, T *gin, int64_t
     if (ntiles > 0) {
         constexpr auto kernel = backward_tiles_kernel<Op, T, U, TileConfig<Op, T>::kMinBlocks>;
         const int64_t want = (ntiles + kWarps - 1) / kWarps;
-        const int64_t cap = (int64_t)sm_count() * resident_ctas<kernel>();
+        const int64_t cap = (int64_t)sm_count() * resident_ctas<kernel>(TileConfig<Op, T>::kMaxCtasPerSm);
         kernel<<<(unsigned)std::min(want, cap), kThreads, 0, stream>>>(state, gout, gin, ntiles,
                                                                        op);
         note_launch();
