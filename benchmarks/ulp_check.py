@@ -1,0 +1,23 @@
+import sys, torch
+sys.path.insert(0, '/root/repo')
+import torch.nn.functional as F
+import fewbit_b200 as fb
+torch.manual_seed(0)
+dev = 'cuda'
+x = torch.cat([torch.randn(1 << 22, device=dev) * 2, torch.randn(1 << 20, device=dev) * 20, torch.linspace(-100, 100, 1 << 20, device=dev),
+               torch.tensor([0.0, -0.0, 1e-30, -1e-30, 1e-8, -1e-8, float('inf'), -float('inf'), float('nan'), 88.0, -88.0, -87.3, -103.0, -104.0, 20.0, 20.000002], device=dev)])
+for name in ['elu', 'celu', 'selu', 'logsigmoid', 'softplus']:
+    y = getattr(fb.functional, name)(x.clone())
+    ref64 = getattr(F, name)(x.double())
+    ref32 = getattr(F, name)(x)
+    fin = torch.isfinite(ref64)
+    sp = (torch.nextafter(ref64.float().abs(), torch.tensor(float('inf'), device=dev)) - ref64.float().abs()).double()
+    ours = ((y.double() - ref64).abs() / sp)[fin]
+    aten = ((ref32.double() - ref64).abs() / sp)[fin]
+    same_nan = bool((torch.isnan(y) == torch.isnan(ref32)).all())
+    print(f'{name:11s} ours max {ours.max().item():.2f} ulp  (ATen fp32 max {aten.max().item():.2f} ulp), vs ATen max {(((y - ref32).abs().double() / sp)[fin]).max().item():.2f} ulp, nan/inf agree {same_nan}, inf agree {bool((torch.isinf(y) == torch.isinf(ref32)).all())}')
+y = fb.functional.softplus(x.clone(), beta=2.5, threshold=7.0)
+ref64 = F.softplus(x.double(), beta=2.5, threshold=7.0)
+fin = torch.isfinite(ref64)
+sp = (torch.nextafter(ref64.float().abs(), torch.tensor(float('inf'), device=dev)) - ref64.float().abs()).double()
+print('softplus beta 2.5: max', (((y.double() - ref64).abs() / sp)[fin]).max().item(), 'ulp')

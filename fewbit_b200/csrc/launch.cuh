@@ -2,6 +2,7 @@
 #pragma once
 
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 
 #include "ops.cuh"
@@ -21,6 +22,9 @@
 #endif
 #ifndef FEWBIT_U_HEAVY
 #define FEWBIT_U_HEAVY 4
+#endif
+#ifndef FEWBIT_TILE_HINTS
+#define FEWBIT_TILE_HINTS 1   // 0: one tile shape for every fp32 forward kernel (A/B builds)
 #endif
 #ifndef FEWBIT_MAX_CTAS_PER_SM
 #define FEWBIT_MAX_CTAS_PER_SM 4
@@ -73,10 +77,18 @@ template <class Op, typename T> struct TileConfig {
     // of the memory system: backward 88 % -> 94-95 % of the HBM peak on a 200 MB tensor, forward
     // 86 % -> 91-93 % (profiles/r01_function_sweep_3bit.md).  The bf16 kernels sit at four anyway.
     static constexpr int kMaxCtasPerSm = FEWBIT_MAX_CTAS_PER_SM;
+    template <class O, typename = void> struct Hint {   // ops without a per-function hint
+        static constexpr int kSubtiles = FEWBIT_U_HEAVY, kMinBlocks = FEWBIT_MINB_HEAVY_F32;
+    };
+    template <class O> struct Hint<O, std::enable_if_t<(O::kSubtilesF32 > 0)>> {
+        static constexpr int kSubtiles = FEWBIT_TILE_HINTS ? O::kSubtilesF32 : FEWBIT_U_HEAVY;
+        static constexpr int kMinBlocks = FEWBIT_TILE_HINTS ? O::kMinBlocksF32 : FEWBIT_MINB_HEAVY_F32;
+    };
     static constexpr int kSubtiles =
-        kHeavy ? FEWBIT_U_HEAVY : (sizeof(T) == 2 ? FEWBIT_U_LIGHT_BF16 : FEWBIT_U_LIGHT_F32);
+        kHeavy ? (sizeof(T) == 4 ? Hint<Op>::kSubtiles : FEWBIT_U_HEAVY)
+               : (sizeof(T) == 2 ? FEWBIT_U_LIGHT_BF16 : FEWBIT_U_LIGHT_F32);
     static constexpr int kMinBlocks =
-        kHeavy ? (sizeof(T) == 2 ? FEWBIT_MINB_HEAVY_BF16 : FEWBIT_MINB_HEAVY_F32) : FEWBIT_MINB_LIGHT;
+        kHeavy ? (sizeof(T) == 2 ? FEWBIT_MINB_HEAVY_BF16 : Hint<Op>::kMinBlocks) : FEWBIT_MINB_LIGHT;
 };
 
 // Resident CTAs per SM for `kernel` (occupancy API, cached per instantiation), overridable

@@ -273,6 +273,9 @@ FEWBIT_HALVES_1(ex2_, ex2_approx(x))
 FEWBIT_HALVES_1(lg2_, lg2_approx(x))
 FEWBIT_HALVES_1(abs_, fabsf(x))
 FEWBIT_HALVES_1(neg_, -x)
+FEWBIT_HALVES_1(expf_, expf(x))                 // libdevice, 2 ulp
+// 2^k from km = k + 1.5 * 2^23 (the "magic" rounding constant): k sits in the low mantissa bits
+FEWBIT_HALVES_1(pow2_of_magic, __uint_as_float((__float_as_uint(x) << 23) + 0x3f800000u))
 #undef FEWBIT_HALVES_1
 __device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
 __device__ __forceinline__ float copysign_(float mag, float sgn) { return copysignf(mag, sgn); }
@@ -371,6 +374,62 @@ template <class L> __device__ __forceinline__ L gelu(L x) {
 }
 }  // namespace fast
 
+namespace accurate {   // fp32-grade replacements of the two costly libdevice calls; L = float or Pair
+// Coefficients and measured error bounds: tools/fit_fp32_math.py.
+//
+// e^z - 1 for z <= 0 (the only range ELU, CELU and SELU need; larger z gives garbage, NaN stays
+// NaN): z = k ln2 + r, |r| <= ln2/2, expm1(r) = r + r^2 Q(r), and
+// e^z - 1 = 2^k expm1(r) + (2^k - 1) in one fused multiply-add -- 2^k - 1 is exact.  0.86 ulp
+// against 29 instructions of expm1f; 13 of the 16 operations here pair up.
+template <class L> __device__ __forceinline__ L expm1_nonpos(L z) {
+    z = if_less(z, lane<L>(-88.0f), lane<L>(-88.0f), z);                 // 2^k would leave the exponent range
+    const L magic = lane<L>(12582912.0f);
+    const L km = fma_(z, lane<L>(1.4426950408889634f), magic);           // k = rint(z log2 e), biased
+    const L k = add_(km, lane<L>(-12582912.0f));
+    L r = fma_(k, lane<L>(-0.693145751953125f), z);                      // Cody-Waite: ln2 = hi + lo
+    r = fma_(k, lane<L>(-1.428606765330187e-06f), r);
+    L q = fma_(lane<L>(1.990645978e-04f), r, lane<L>(1.394211431e-03f));
+    q = fma_(q, r, lane<L>(8.333287202e-03f));
+    q = fma_(q, r, lane<L>(4.166634008e-02f));
+    q = fma_(q, r, lane<L>(1.666666716e-01f));
+    q = fma_(q, r, lane<L>(5.000000000e-01f));
+    const L p = fma_(mul_(r, r), q, r);
+    const L t = pow2_of_magic(km);
+    return fma_(t, p, add_(t, lane<L>(-1.0f)));
+}
+// log(1 + e) for e in (0, 1] (softplus and logsigmoid call it with e = exp(-|x|)):
+// 2 atanh(s), s = e / (2 + e) <= 1/3, as 2 s + s^3 R(s^2); the quotient from MUFU.RCP, one Newton
+// step and a residual correction (correctly rounded s).  1.1 ulp against ~30 instructions of log1pf.
+template <class L> __device__ __forceinline__ L log1p_unit(L e) {
+    const L d = add_(e, lane<L>(2.0f)), one = lane<L>(1.0f);
+    const L y0 = rcp_(d);
+    const L y = fma_(fma_(neg_(d), y0, one), y0, y0);
+    L s = mul_(e, y);
+    // residual e - s (2 + e) against the TRUE denominator (d itself is rounded): e - 2 s is exact
+    s = fma_(fma_(neg_(s), e, fma_(lane<L>(-2.0f), s, e)), y, s);
+    const L u = mul_(s, s);
+    L q = fma_(lane<L>(2.093757242e-01f), u, lane<L>(1.742623448e-01f));
+    q = fma_(q, u, lane<L>(2.226814181e-01f));
+    q = fma_(q, u, lane<L>(2.857018113e-01f));
+    q = fma_(q, u, lane<L>(4.000001252e-01f));
+    q = fma_(q, u, lane<L>(6.666666865e-01f));
+    return fma_(mul_(s, u), q, add_(s, s));
+}
+template <class L> __device__ __forceinline__ L elu(L x, float pos, float neg, float in_scale) {
+    return if_greater(x, lane<L>(0.0f), mul_(x, lane<L>(pos)),
+                      mul_(expm1_nonpos(mul_(x, lane<L>(in_scale))), lane<L>(neg)));
+}
+// min(0, x) - log1p(exp(-|x|)): ATen's own expression
+template <class L> __device__ __forceinline__ L logsigmoid(L x) {
+    return add_(min_(x, lane<L>(0.0f)), neg_(log1p_unit(expf_(neg_(abs_(x))))));
+}
+// log1p(exp(z)) = max(z, 0) + log1p(exp(-|z|)), z = beta x: no overflow, and the logarithm's
+// argument stays in (1, 2]
+template <class L> __device__ __forceinline__ L softplus_of_scaled(L z) {
+    return add_(if_greater(z, lane<L>(0.0f), z, lane<L>(0.0f)), log1p_unit(expf_(neg_(abs_(z)))));
+}
+}  // namespace accurate
+
 // A functor with a bf16 formula exposes it for one element and for a pair.
 // PAIRED says whether the tile kernel uses the pair form: measured per function on B200
 // (profiles/r01_function_sweep_3bit.md) -- it pays where the formula is mostly multiply-adds
@@ -383,13 +442,24 @@ template <class L> __device__ __forceinline__ L gelu(L x) {
         unpair(CALL2, x0, x1);                                                                 \
     }
 
+// The same for an fp32 formula built from the accurate:: helpers (always used in pair form by the
+// tile kernel: these formulas are multiply-add chains).
+#define FEWBIT_F32_FORMULA(CALL1, CALL2)                                                       \
+    static constexpr bool kPaired32 = true;                                                    \
+    __device__ __forceinline__ float f32_value(float x) const { return CALL1; }               \
+    __device__ __forceinline__ void f32_pair(float &x0, float &x1) const {                     \
+        const Pair x = pair(x0, x1);                                                           \
+        unpair(CALL2, x0, x1);                                                                 \
+    }
+
 struct EluFamily {  // celu / elu / selu:  x > 0 ? x*pos : expm1(x*in_scale)*neg
     float pos, neg, in_scale;
     template <typename T> __device__ __forceinline__ float eval(float x) const {
         if constexpr (sizeof(T) == 2) return bf16_value(x);
-        return x > 0.0f ? x * pos : expm1f(x * in_scale) * neg;
+        return f32_value(x);
     }
     FEWBIT_BF16_FORMULA(true, fast::elu<float>(x, pos, neg, in_scale), fast::elu<Pair>(x, pos, neg, in_scale))
+    FEWBIT_F32_FORMULA(accurate::elu<float>(x, pos, neg, in_scale), accurate::elu<Pair>(x, pos, neg, in_scale))
 };
 struct CeluFn : EluFamily {  // codec.cu:517-526
     __host__ CeluFn(double alpha, double) : EluFamily{1.0f, (float)alpha, (float)(1.0 / alpha)} {}
@@ -436,9 +506,10 @@ struct LogSigmoidFn {  // codec.cu:566-576
     __host__ LogSigmoidFn(double, double) {}
     template <typename T> __device__ __forceinline__ float eval(float x) const {
         if constexpr (sizeof(T) == 2) return bf16_value(x);
-        return fminf(0.0f, x) - log1pf(expf(-fabsf(x)));
+        return f32_value(x);
     }
     FEWBIT_BF16_FORMULA(true, fast::logsigmoid<float>(x), fast::logsigmoid<Pair>(x))
+    FEWBIT_F32_FORMULA(accurate::logsigmoid<float>(x), accurate::logsigmoid<Pair>(x))
 };
 struct MishFn {  // codec.cu:578-586
     // tanh(log(1 + e)) = ((1+e)^2 - 1) / ((1+e)^2 + 1) = n / (n + 2) with n = e (e + 2), e = e^x:
@@ -476,9 +547,22 @@ struct SoftplusFn {  // codec.cu:616-632
         : beta((float)b), threshold((float)t), inv_beta((float)(1.0 / b)), unit_beta((float)b == 1.0f) {}
     template <typename T> __device__ __forceinline__ float eval(float x) const {
         if constexpr (sizeof(T) == 2) return bf16_value(x);
-        const float bx = x * beta;
-        const float soft = log1pf(expf(bx));
-        return bx > threshold ? x : (unit_beta ? soft : soft / beta);   // x / 1 is exact: skip it
+        return f32_value(x);
+    }
+    // ATen: x * beta > threshold ? x : log1p(exp(x * beta)) / beta  (x / 1 is exact: skipped)
+    __device__ __forceinline__ float f32_value(float x) const {
+        const float bx = x * beta, soft = accurate::softplus_of_scaled<float>(bx);
+        return bx > threshold ? x : (unit_beta ? soft : soft / beta);
+    }
+    static constexpr bool kPaired32 = true;
+    __device__ __forceinline__ void f32_pair(float &x0, float &x1) const {
+        const Pair bx = mul_(pair(x0, x1), lane<Pair>(beta));
+        float b0, b1, s0, s1;
+        unpair(bx, b0, b1);
+        unpair(accurate::softplus_of_scaled<Pair>(bx), s0, s1);
+        if (!unit_beta) s0 = s0 / beta, s1 = s1 / beta;
+        x0 = b0 > threshold ? x0 : s0;
+        x1 = b1 > threshold ? x1 : s1;
     }
     FEWBIT_BF16_FORMULA(false, fast::softplus<float>(x, beta, threshold, inv_beta),
                         fast::softplus<Pair>(x, beta, threshold, inv_beta))
@@ -514,9 +598,36 @@ struct TanhshrinkFn {  // codec.cu:648-653
 #endif
 template <class Fn, typename = void> struct has_pairs : std::false_type {};
 template <class Fn> struct has_pairs<Fn, std::enable_if_t<Fn::kPaired>> : std::true_type {};
+template <class Fn, typename = void> struct has_pairs32 : std::false_type {};
+template <class Fn> struct has_pairs32<Fn, std::enable_if_t<Fn::kPaired32>> : std::true_type {};
+
+// Tile shape of the fp32 forward kernel per function: (subtiles per warp tile, resident CTAs the
+// register budget is set for).  Measured on B200 over {1,4}, {2,4}, {2,3}, {4,3} for every function
+// (3-bit, 128x128x3072; profiles/r01_function_sweep_3bit.md): short formulas want few loads in flight
+// per warp and four CTAs, libdevice-heavy ones the registers of three CTAs.
+template <class Fn> struct TileHintF32 {
+    static constexpr int kSubtiles = 4, kMinBlocks = 3;               // gelu, logsigmoid
+};
+#define FEWBIT_TILE_HINT_F32(FN, U, MINB)                                 \
+    template <> struct TileHintF32<FN> {                                  \
+        static constexpr int kSubtiles = U, kMinBlocks = MINB;            \
+    };
+FEWBIT_TILE_HINT_F32(CeluFn, 1, 4)
+FEWBIT_TILE_HINT_F32(EluFn, 1, 4)
+FEWBIT_TILE_HINT_F32(SeluFn, 1, 4)
+FEWBIT_TILE_HINT_F32(HardswishFn, 1, 4)
+FEWBIT_TILE_HINT_F32(SoftsignFn, 2, 3)
+FEWBIT_TILE_HINT_F32(TanhFn, 2, 3)
+FEWBIT_TILE_HINT_F32(TanhshrinkFn, 2, 3)
+FEWBIT_TILE_HINT_F32(SigmoidFn, 2, 3)
+FEWBIT_TILE_HINT_F32(MishFn, 2, 3)
+FEWBIT_TILE_HINT_F32(SiluFn, 2, 4)
+FEWBIT_TILE_HINT_F32(SoftplusFn, 2, 4)
+#undef FEWBIT_TILE_HINT_F32
 
 template <class Fn, typename T, int B> struct QuantizeOp {
     static constexpr int kBits = B;
+    static constexpr int kSubtilesF32 = TileHintF32<Fn>::kSubtiles, kMinBlocksF32 = TileHintF32<Fn>::kMinBlocks;
     static constexpr bool kHeavy = true;  // transcendental math: see TileConfig in launch.cuh
     using Scratch = typename Bucketizer<T, B>::Scratch;
     Fn fn;
@@ -527,6 +638,9 @@ template <class Fn, typename T, int B> struct QuantizeOp {
         if constexpr (sizeof(T) == 2 && has_pairs<Fn>::value && FEWBIT_PAIRS) {
 #pragma unroll
             for (int j = 0; j < 8; j += 2) fn.bf16_pair(v[j], v[j + 1]);
+        } else if constexpr (sizeof(T) == 4 && has_pairs32<Fn>::value && FEWBIT_PAIRS) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) fn.f32_pair(v[j], v[j + 1]);
         } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = fn.template eval<T>(v[j]);
