@@ -1,5 +1,11 @@
-import sys, torch
-sys.path.insert(0, '/root/repo')
+"""Worst error in ulps of the fp32 ELU family, logsigmoid and softplus against float64 (and of ATen's
+own fp32 kernels, for scale) on ~6 M points incl. special values."""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import torch.nn.functional as F
 import fewbit_b200 as fb
 torch.manual_seed(0)
