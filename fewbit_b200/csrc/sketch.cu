@@ -2,7 +2,7 @@
 //
 //   X   : [N tokens, D features] bf16, row-major (TMA source; never copied or transposed)
 //   S   : [P, N] random sketch, N(0,1) or +-1/2 entries, NEVER materialised: every element is
-//         a pure function of (seed, offset, p, n) -- Philox4x32-10 keyed by the seed; one call
+//         a pure function of (seed, offset, p, n) -- Philox4x32-7 keyed by the seed; one call
 //         with counter (n / 8, p, offset) gives eight normals (Box-Muller on 16-bit uniforms),
 //         one call with counter (n / 128, p, offset) gives 128 signs -- so forward and backward
 //         regenerate the same S.
@@ -247,12 +247,21 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
 
 // ------------------------------------------------------------------------- random ----
 
+// Philox4x32 with 7 rounds: the shortest variant that passes BigCrush (Salmon et al., "Parallel
+// random numbers: as easy as 1, 2, 3", SC'11, table 2); cuRAND's 10 rounds add a safety margin a
+// sketching matrix does not need, and the rounds are a third of the generators' instructions.
+// -DFEWBIT_PHILOX_ROUNDS=10 restores it (S changes, nothing else does).
+#ifndef FEWBIT_PHILOX_ROUNDS
+#define FEWBIT_PHILOX_ROUNDS 7
+#endif
+constexpr int kPhiloxRounds = FEWBIT_PHILOX_ROUNDS;
+
 struct Philox {
     uint32_t k0, k1;
     __device__ __forceinline__ uint4 operator()(uint4 c) const {
         uint32_t a = k0, b = k1;
 #pragma unroll
-        for (int round = 0; round < 10; ++round) {
+        for (int round = 0; round < kPhiloxRounds; ++round) {
             const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
             const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
             c = make_uint4(hi1 ^ c.y ^ a, lo1, hi0 ^ c.w ^ b, lo0);
@@ -302,7 +311,7 @@ __device__ __forceinline__ void normal_octet2(const Philox &rng, uint32_t o0, ui
     uint4 c0 = make_uint4(o0, p0, off_lo, off_hi), c1 = make_uint4(o1, p1, off_lo, off_hi);
     uint32_t a = rng.k0, b = rng.k1;
 #pragma unroll
-    for (int round = 0; round < 10; ++round) {
+    for (int round = 0; round < kPhiloxRounds; ++round) {
         const uint32_t h00 = __umulhi(0xD2511F53u, c0.x), l00 = 0xD2511F53u * c0.x;
         const uint32_t h10 = __umulhi(0xD2511F53u, c1.x), l10 = 0xD2511F53u * c1.x;
         const uint32_t h01 = __umulhi(0xCD9E8D57u, c0.z), l01 = 0xCD9E8D57u * c0.z;
