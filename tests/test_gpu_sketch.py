@@ -41,7 +41,9 @@ def test_sketch_matrix_statistics(kind):
 
 
 SHAPES = [(64, 8, 16), (1000, 72, 50), (4096, 384, 160), (4100, 392, 161), (2048, 768, 333),
-          (16384, 768, 3276), (3000, 3072, 600), (777, 1024, 1)]
+          (16384, 768, 3276), (3000, 3072, 600), (777, 1024, 1),
+          # feature counts that are multiples of 768 run on CTA pairs (Gaussian): edge shapes of that mode
+          (100, 768, 1), (64, 1536, 17), (130, 2304, 161), (8200, 768, 145)]
 
 
 @pytest.mark.parametrize('tokens,features,rows', SHAPES)
