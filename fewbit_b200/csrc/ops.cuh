@@ -189,8 +189,9 @@ template <typename T, int B> struct Bucketizer<T, B, false> {
 
 // =====================================================================================
 // Continuous activations.  fp32: the expressions ATen's CUDA kernels use in fp32 opmath (that is
-// what the reference's test compares against: functional/activations_test.py:88-89) with the
-// accurate libdevice functions (mish and softplus/beta=1 rearranged, still within 4 ulp).
+// what the reference's test compares against: functional/activations_test.py:88-89) with accurate
+// functions -- libdevice, or `namespace accurate` below for expm1 and log1p (mish and softplus
+// rearranged); every result within 3 ulp of ATen's, gelu bit for bit.
 // bf16: inputs are widened to fp32, evaluated with the MUFU-based forms below (a bf16 kernel
 // moves half the bytes per element, so libdevice-grade math would make it compute-bound at
 // 26-50 % of HBM speed) and rounded once.  Reference lambdas: fewbit/cuda/codec.cu:517-653.
