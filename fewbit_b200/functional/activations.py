@@ -89,8 +89,10 @@ def make_table(name: str, bits: int, scale: float = 1.5) -> Tuple[T.Tensor, T.Te
     N(0, scale^2) with the +-100 sentinels, levels = the mean derivative on each interval,
     ``diff(f(borders)) / diff(borders)`` -- the optimal levels for given borders
     (reference ``fewbit/approx.py:116,132``).  The reference ships tables for 1..4 bits only
-    (``tools/quantize-builtins.sh:8``); this covers the 5..8-bit sweeps.  float64, same layout
-    as the built-in ones; pass as ``borders=``/``values=`` or ``store.add(name, bits, ...)``.
+    (``tools/quantize-builtins.sh:8``).  A cheap stand-in for arbitrary functions and parameters;
+    the optimal tables come from ``fewbit_b200.quantize.optimal_table`` (the 5..8-bit ones of the
+    13 built-in functions are shipped in ``data/extended.npz``).  float64, same layout as the
+    built-in ones; pass as ``borders=``/``values=`` or ``store.add(name, bits, ...)``.
     """
     count = (1 << bits) - 1
     probs = T.arange(1, count + 1, dtype=T.float64) / (count + 1)
@@ -102,7 +104,13 @@ def make_table(name: str, bits: int, scale: float = 1.5) -> Tuple[T.Tensor, T.Te
 
 
 store = StepwiseStore()
+# bits 1..4: the reference's own tables, number for number (tools/make_builtin_tables.py);
+# bits 5..8: optimal tables for the same objective from fewbit_b200/quantize.py
+# (tools/make_extended_tables.py) -- the reference ships none, its kernels stop being useful there.
 store.load(Path(__file__).resolve().parent.parent / 'data' / 'builtin.npz')
+_extended = Path(__file__).resolve().parent.parent / 'data' / 'extended.npz'
+if _extended.exists():
+    store.load(_extended)
 
 
 # ------------------------------------------------------------------ device dispatch ----

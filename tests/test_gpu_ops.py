@@ -136,6 +136,25 @@ def test_fp32_own_expm1_and_log1p_against_float64(name, bound):
     assert apart <= 3.0, f'{name}: {apart:.2f} ulp from ATen'
 
 
+@pytest.mark.parametrize('name', ['gelu', 'selu', 'softsign', 'hardswish'])
+@pytest.mark.parametrize('bits', [5, 6, 7, 8])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_shipped_5_to_8_bit_tables_through_the_kernels(name, bits, dtype):
+    """`fewbit.GELU(bits=6)` and friends: the optimal 5..8-bit tables of data/extended.npz, cast like
+    the built-in ones, give exactly levels[#{bounds < x}] * g -- including the two softsign tables
+    whose borders crowd the bucket LUT (exact-search fallback) and the tables with a border on a
+    jump of the derivative (selu at 0, hardswish at +-3)."""
+    torch.manual_seed(bits)
+    x = (torch.randn(100003, device=DEV) * 3).to(dtype)
+    x[:5] = torch.tensor([0.0, -0.0, 3.0, -3.0, 100.0], device=DEV).to(dtype)
+    g = torch.randn(100003, device=DEV).to(dtype)
+    leaf = x.clone().requires_grad_()
+    getattr(FF, name)(leaf, bits=bits).backward(g)
+    borders, levels = store.get(name, bits, DEV, dtype)
+    codes = torch.searchsorted(borders[1:-1].contiguous(), x)
+    assert torch.equal(leaf.grad, levels[codes] * g)
+
+
 # ---- operator semantics -------------------------------------------------------------------
 
 def test_in_place_and_only_codes_are_saved():

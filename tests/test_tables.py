@@ -12,16 +12,17 @@ OURS = Path(__file__).resolve().parents[1] / 'fewbit_b200' / 'data' / 'builtin.n
 
 
 def test_store_is_complete():
-    # 13 functions x bits 1..4 (tools/quantize-builtins.sh:8 of the reference)
-    assert len(store) == 52
+    # 13 functions x bits 1..4: the reference's tables (tools/quantize-builtins.sh:8 of the reference);
+    # bits 5..8: optimal tables from fewbit_b200/quantize.py (the reference ships none)
+    assert len(store) == 104
     for name in CONTINOUS:
-        for bits in range(1, 5):
+        for bits in range(1, 9):
             borders, levels = store.get(name, bits)
             assert borders.numel() == 2 ** bits + 1 and levels.numel() == 2 ** bits
             assert borders[0] == -100 and borders[-1] == 100
             assert torch.all(borders[1:] > borders[:-1])
     with pytest.raises(KeyError):
-        store.get('gelu', 5)
+        store.get('gelu', 9)
 
 
 def test_store_caches_per_device_and_dtype():
