@@ -230,3 +230,52 @@ def ref_ops_path() -> Path | None:
     """
     path = HERE / '_ref' / 'libfewbit_ref.so'
     return path if path.exists() else None
+
+
+# ------------------------------------------------------------------ sketch entries ----
+# The projection's random matrix S is OUR definition (the reference draws torch.randn; SURVEY 8c:
+# "the bit pattern of S is parity unpinned"), so the oracle restates it: Philox4x32 with
+# PHILOX_ROUNDS rounds (Salmon et al., SC'11: multipliers 0xD2511F53 / 0xCD9E8D57, key increments
+# 0x9E3779B9 / 0xBB67AE85), key = the 64-bit seed, counter = (column block, row, offset lo, offset hi).
+# Rademacher: counter column block = n // 128, bit b of output word w is entry 128 (n // 128) +
+# 32 w + b, set bit = +1/2, clear bit = -1/2.  Gaussian: column block = n // 8, each output word
+# gives two normals by Box-Muller on its two 16-bit halves ((h + 1/2) / 65536): low half -> radius
+# sqrt(-2 ln u), high half -> angle 2 pi u; entries 2 w (cos) and 2 w + 1 (sin) of the octet.
+# fewbit_b200/csrc/sketch.cu: Philox, normal_pair, sign_pair, sketch_matrix_kernel.
+PHILOX_ROUNDS = 7
+
+
+def philox4x32(counter: np.ndarray, seed: int, rounds: int = PHILOX_ROUNDS) -> np.ndarray:
+    """counter: uint32 [..., 4] -> uint32 [..., 4]."""
+    c = np.asarray(counter, dtype=np.uint64).copy()
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(rounds):
+        p0 = np.uint64(0xD2511F53) * c[..., 0]
+        p1 = np.uint64(0xCD9E8D57) * c[..., 2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c = np.stack([hi1 ^ c[..., 1] ^ k0, lo1, hi0 ^ c[..., 3] ^ k1, lo0], axis=-1)
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    return c.astype(np.uint32)
+
+
+def sketch_matrix(rows: int, cols: int, seed: int, offset: int, kind: str = 'rademacher') -> np.ndarray:
+    """S as float64 [rows, cols]: exact for 'rademacher' (+-1/2); for 'gaussian' the ideal Box-Muller
+    values before the kernel's MUFU approximations and bf16 rounding."""
+    p = np.arange(rows, dtype=np.uint64)[:, None]
+    lo, hi = offset & 0xFFFFFFFF, (offset >> 32) & 0xFFFFFFFF
+    if kind == 'rademacher':
+        blocks = np.arange((cols + 127) // 128, dtype=np.uint64)[None, :]
+        counter = np.stack(np.broadcast_arrays(blocks, p, np.uint64(lo), np.uint64(hi)), axis=-1)
+        words = philox4x32(counter, seed)                                   # [rows, blocks, 4]
+        bits = (words[..., None] >> np.arange(32, dtype=np.uint32)) & 1      # [rows, blocks, 4, 32]
+        return (bits.reshape(rows, -1)[:, :cols].astype(np.float64) - 0.5)
+    octets = np.arange((cols + 7) // 8, dtype=np.uint64)[None, :]
+    counter = np.stack(np.broadcast_arrays(octets, p, np.uint64(lo), np.uint64(hi)), axis=-1)
+    words = philox4x32(counter, seed).astype(np.float64)                    # [rows, octets, 4]
+    u_radius = ((words.astype(np.uint64) & 0xFFFF) + 0.5) / 65536.0
+    u_angle = ((words.astype(np.uint64) >> 16) + 0.5) / 65536.0
+    radius, angle = np.sqrt(-2.0 * np.log(u_radius)), 2.0 * np.pi * u_angle
+    pairs = np.stack([radius * np.cos(angle), radius * np.sin(angle)], axis=-1)   # [rows, octets, 4, 2]
+    return pairs.reshape(rows, -1)[:, :cols]

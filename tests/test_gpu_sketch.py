@@ -4,6 +4,7 @@ S is never materialised by the product; `sketch_matrix` reproduces it with the s
 function so that the kernel can be checked against a plain fp32 torch matmul of the same S
 (tolerance 2e-3 of the result's RMS: bf16 operands are exact in the fp32 products, only the
 accumulation order differs)."""
+import numpy as np
 import pytest
 import torch
 
@@ -44,6 +45,20 @@ SHAPES = [(64, 8, 16), (1000, 72, 50), (4096, 384, 160), (4100, 392, 161), (2048
           (16384, 768, 3276), (3000, 3072, 600), (777, 1024, 1),
           # feature counts that are multiples of 768 run on CTA pairs (Gaussian): edge shapes of that mode
           (100, 768, 1), (64, 1536, 17), (130, 2304, 161), (8200, 768, 145)]
+
+
+@pytest.mark.parametrize('rows,cols,seed,offset', [(5, 300, 42, 4), (161, 4100, 2 ** 40 + 3, 2 ** 33 + 9),
+                                                   (3, 128, 0, 0)])
+def test_sketch_entries_match_the_oracle(rows, cols, seed, offset):
+    """S entry by entry against the numpy restatement (oracle.sketch_matrix): Rademacher bit for
+    bit -- that pins the counter layout (column block, row, 64-bit offset) and the 64-bit key;
+    Gaussian to the accuracy of the kernel's MUFU Box-Muller plus one bf16 rounding."""
+    import oracle
+    got = native.sketch_matrix(rows, cols, seed, offset, 'rademacher').float().cpu().numpy()
+    assert np.array_equal(got, oracle.sketch_matrix(rows, cols, seed, offset, 'rademacher'))
+    got = native.sketch_matrix(rows, cols, seed, offset, 'gaussian').float().cpu().numpy()
+    want = oracle.sketch_matrix(rows, cols, seed, offset, 'gaussian')
+    assert np.all(np.abs(got - want) <= np.abs(want) * 2.0 ** -7 + 1e-3)
 
 
 @pytest.mark.parametrize('tokens,features,rows', SHAPES)

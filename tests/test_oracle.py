@@ -184,3 +184,31 @@ def test_empty_inputs():
     assert oracle.stepwise_backward(state, np.zeros(0, np.float32), LEVELS).size == 0
     y, state = oracle.piecewise_forward('relu', np.zeros(0, np.float32))
     assert y.size == 0 and state.size == 0
+
+
+# ---- sketch entries (the projection's S is defined by this package: pinned here) ------------
+
+def test_philox4x32_known_answers():
+    """Random123's published known-answer vectors for philox4x32-10 (kat_vectors: zero, all-ones and
+    pi-digit counter/key) pin the restated round function; the kernels run the same rounds, seven
+    of them (oracle.PHILOX_ROUNDS)."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff, ) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for counter, key, want in kat:
+        got = oracle.philox4x32(np.array([counter], dtype=np.uint32), key[0] | (key[1] << 32), rounds=10)
+        assert tuple(int(v) for v in got[0]) == want
+    assert oracle.PHILOX_ROUNDS == 7
+
+
+def test_oracle_sketch_matrix_statistics():
+    r = oracle.sketch_matrix(64, 4096, 42, 4, 'rademacher')
+    assert set(np.unique(r)) == {-0.5, 0.5} and abs(r.mean()) < 0.01
+    g = oracle.sketch_matrix(64, 4096, 42, 4, 'gaussian')
+    assert abs(g.mean()) < 0.01 and abs(g.std() - 1.0) < 0.01
+    assert abs(np.corrcoef(g[:, :-1].ravel(), g[:, 1:].ravel())[0, 1]) < 0.01
+    # a different offset or seed is a different matrix; the same pair reproduces it
+    assert not np.array_equal(r, oracle.sketch_matrix(64, 4096, 42, 5, 'rademacher'))
+    assert not np.array_equal(r, oracle.sketch_matrix(64, 4096, 43, 4, 'rademacher'))
+    assert np.array_equal(r, oracle.sketch_matrix(64, 4096, 42, 4, 'rademacher'))
