@@ -9,4 +9,4 @@ from .activations import (  # noqa: F401
 from .activations import (  # noqa: F401
     CONTINOUS, CONTINUOUS, STEPWISE, StepwiseStore, make_table, store)
 # Linear layer with randomized (sketched) weight gradient.
-from .linear import linear_grp, linear_randomized  # noqa: F401
+from .linear import linear_crs, linear_grp, linear_randomized  # noqa: F401

@@ -20,7 +20,7 @@ from typing import Literal, Optional
 import torch as T
 import torch.nn.functional as F
 
-__all__ = ('linear_grp', 'linear_randomized', 'calc_proj_dim')
+__all__ = ('linear_crs', 'linear_grp', 'linear_randomized', 'calc_proj_dim')
 
 MatMulType = Literal['gaussian', 'rademacher', 'dct', 'dft']
 
@@ -190,3 +190,41 @@ class LinearGRPFunc(T.autograd.Function):
 
 linear_grp = LinearGRPFunc.apply
 linear_randomized = linear_grp
+
+
+class LinearCRSFunc(T.autograd.Function):
+    """Linear layer whose weight gradient comes from column-row sampling over the input FEATURES
+    (reference ``fewbit/functional/linear.py:27-66``): ``nopairs`` feature indices are drawn
+    uniformly with replacement, the distinct ones are kept with weight ``count * in_features /
+    nopairs``, and only those columns of the input are saved.  The forward result is exact; the
+    weight gradient is unbiased, zero outside the sampled columns.  Plain PyTorch on either device
+    (a gather and a small product -- no kernel of its own); the indices are drawn from the CPU
+    default generator like the reference does, so the same seed selects the same columns.
+    """
+
+    @staticmethod
+    def forward(ctx, input: T.Tensor, weight: T.Tensor, bias: Optional[T.Tensor], nopairs: int) -> T.Tensor:
+        in_features = weight.shape[1]
+        draws = T.randint(0, in_features, (nopairs, )).to(weight.device)
+        hits = T.bincount(draws, minlength=in_features)
+        pairs = T.nonzero(hits, as_tuple=True)[0]
+        scale = hits[pairs].to(T.float32) * (in_features / nopairs)
+        ctx.save_for_backward(input[..., pairs] * scale.to(input.dtype), weight, bias, pairs)
+        return _linear_owning_output(input.reshape(-1, in_features), weight, bias, input.shape)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input_proj, weight, bias, pairs = ctx.saved_tensors
+        grad_input = grad_weight = grad_bias = None
+        grad_view = grad_output.reshape(-1, grad_output.shape[-1])
+        if ctx.needs_input_grad[0]:
+            grad_input = grad_output @ weight
+        if ctx.needs_input_grad[1]:
+            grad_weight = T.zeros_like(weight)
+            grad_weight[:, pairs] = grad_view.T @ input_proj.reshape(-1, input_proj.shape[-1])
+        if bias is not None and ctx.needs_input_grad[2]:
+            grad_bias = grad_view.sum(dim=0)
+        return grad_input, grad_weight, grad_bias, None
+
+
+linear_crs = LinearCRSFunc.apply

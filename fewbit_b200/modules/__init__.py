@@ -5,9 +5,9 @@ from .activations import (  # noqa: F401
 from .activations import (  # noqa: F401
     CELU, ELU, GELU, Hardswish, LogSigmoid, Mish, SELU, Sigmoid, SiLU, Softplus, Softsign, Tanh,
     Tanhshrink)
-from .linear import LinearGRP, RandomizedLinear  # noqa: F401
+from .linear import LinearCRS, LinearGRP, RandomizedLinear  # noqa: F401
 
 __all__ = ('Hardshrink', 'Hardsigmoid', 'Hardtanh', 'LeakyReLU', 'ReLU', 'ReLU6', 'Softshrink',
            'Stepwise', 'Threshold', 'CELU', 'ELU', 'GELU', 'Hardswish', 'LogSigmoid', 'Mish',
-           'SELU', 'Sigmoid', 'SiLU', 'Softplus', 'Softsign', 'Tanh', 'Tanhshrink', 'LinearGRP',
-           'RandomizedLinear')
+           'SELU', 'Sigmoid', 'SiLU', 'Softplus', 'Softsign', 'Tanh', 'Tanhshrink', 'LinearCRS',
+           'LinearGRP', 'RandomizedLinear')

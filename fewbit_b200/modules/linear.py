@@ -5,11 +5,33 @@ from typing import Literal, Optional
 
 import torch as T
 
-from ..functional.linear import linear_grp
+from ..functional.linear import linear_crs, linear_grp
 
-__all__ = ('LinearGRP', 'RandomizedLinear')
+__all__ = ('LinearCRS', 'LinearGRP', 'RandomizedLinear')
 
 MatMulType = Literal['gaussian', 'rademacher', 'dct', 'dft']
+
+
+class LinearCRS(T.nn.Linear):
+    """``torch.nn.Linear`` whose weight gradient is estimated by column-row sampling and which keeps
+    only the sampled input columns for backward (reference ``fewbit/modules/linear.py:16-36``).
+
+    ``proj_dim`` is the number of draws (default ``out_features // 2``).  Two slips of the
+    reference are not reproduced: it passes ``proj_dim`` to ``torch.nn.Linear`` in the place of
+    ``bias`` (so ``bias=False`` is ignored whenever ``proj_dim`` is given), and its ``extra_repr``
+    reads an attribute that does not exist.
+    """
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, device=None, dtype=None,
+                 proj_dim: Optional[int] = None) -> None:
+        super().__init__(in_features, out_features, bias, device, dtype)
+        self.proj_dim: int = proj_dim or out_features // 2
+
+    def forward(self, input: T.Tensor) -> T.Tensor:
+        return linear_crs(input, self.weight, self.bias, self.proj_dim)
+
+    def extra_repr(self) -> str:
+        return f'{super().extra_repr()}, proj_dim={self.proj_dim}'
 
 
 class LinearGRP(T.nn.Linear):

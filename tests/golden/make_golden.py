@@ -146,6 +146,28 @@ def main():
             lin[f'{key}/y'] = y.detach().numpy()
             lin[f'{key}/grad_input'] = x.grad.numpy()
             lin[f'{key}/grad_weight'] = layer.weight.grad.numpy()
+    # LinearCRS (fewbit/functional/linear.py:27-66).  The module's constructor passes proj_dim in the
+    # place of `bias`, so the functional form is called on explicit parameters.
+    from fewbit.functional.linear import linear_crs
+    for bias in (False, True):
+        torch.manual_seed(42)
+        weight = torch.randn(12, 24, requires_grad=True)
+        b = torch.randn(12, requires_grad=True) if bias else None
+        x = torch.randn(4, 10, 24, requires_grad=True)
+        gy = torch.randn(4, 10, 12)
+        torch.manual_seed(1234)  # fixes the sampled columns
+        y = linear_crs(x, weight, b, 16)
+        y.backward(gy)
+        key = f'crs-{int(bias)}'
+        lin[f'{key}/weight'] = weight.detach().numpy()
+        if bias:
+            lin[f'{key}/bias'] = b.detach().numpy()
+            lin[f'{key}/grad_bias'] = b.grad.numpy()
+        lin[f'{key}/x'] = x.detach().numpy()
+        lin[f'{key}/gy'] = gy.numpy()
+        lin[f'{key}/y'] = y.detach().numpy()
+        lin[f'{key}/grad_input'] = x.grad.numpy()
+        lin[f'{key}/grad_weight'] = weight.grad.numpy()
     np.savez_compressed(ROOT / 'tests/golden/reference_linear.npz', **lin)
     print('fixtures:', len(specs), 'op cases,', len(tables), 'table arrays,', len(lin), 'linear arrays')
 

@@ -117,3 +117,52 @@ def test_output_can_be_modified_in_place():
     z = y.relu_()                      # any in-place op on the output
     z.sum().backward()
     assert layer.weight.grad is not None and x.grad is not None
+
+
+# ---- LinearCRS (column-row sampling; reference fewbit/functional/linear.py:27-66) -----------
+
+@pytest.mark.parametrize('bias', [False, True])
+def test_crs_matches_the_reference_on_cpu(golden_linear, bias):
+    """Same seed -> same sampled columns -> the reference's y / grad_input / grad_weight / grad_bias
+    (fixture: tests/golden/make_golden.py ran the reference's linear_crs).  The forward and
+    grad_input are plain products and must agree to the bit; grad_weight is one product computed
+    in a different association (reshape + matmul here, einsum there): 1e-6 relative."""
+    key = f'crs-{int(bias)}'
+    g = {k.split('/', 1)[1]: torch.from_numpy(v) for k, v in golden_linear.items() if k.startswith(key + '/')}
+    layer = fewbit.modules.LinearCRS(24, 12, bias, proj_dim=16)
+    assert (layer.bias is not None) == bias            # the reference ignores `bias` here (its slip)
+    with torch.no_grad():
+        layer.weight.copy_(g['weight'])
+        if bias:
+            layer.bias.copy_(g['bias'])
+    x = g['x'].clone().requires_grad_()
+    torch.manual_seed(1234)
+    y = layer(x)
+    y.backward(g['gy'])
+    torch.testing.assert_close(y.detach(), g['y'], rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(x.grad, g['grad_input'], rtol=0, atol=0)
+    torch.testing.assert_close(layer.weight.grad, g['grad_weight'], rtol=1e-5, atol=1e-5)
+    assert torch.equal(layer.weight.grad == 0, g['grad_weight'] == 0)      # same sampled columns
+    if bias:
+        torch.testing.assert_close(layer.bias.grad, g['grad_bias'], rtol=1e-6, atol=1e-6)
+    assert 'proj_dim=16' in repr(layer)
+
+
+def test_crs_weight_gradient_is_unbiased():
+    """The reference's statistical test (fewbit/modules/linear_test.py:57-92) for LinearCRS:
+    averaged over many draws the sampled gradient approaches the exact one."""
+    torch.manual_seed(42)
+    layer = fewbit.modules.LinearCRS(8, 4, True, proj_dim=64)
+    exact = torch.nn.Linear(8, 4)
+    exact.load_state_dict(layer.state_dict())
+    x = torch.randn(128, 8)
+    exact(x).backward(torch.ones(128, 4))
+    total = torch.zeros_like(layer.weight)
+    repeat = 512
+    for _ in range(repeat):
+        layer.zero_grad()
+        layer(x).backward(torch.ones(128, 4))
+        total += layer.weight.grad
+    rel = torch.linalg.norm(total / repeat - exact.weight.grad) / torch.linalg.norm(exact.weight.grad)
+    assert rel.item() < 0.1
+    assert hasattr(fewbit.functional, 'linear_crs') and fewbit.LinearCRS is fewbit.modules.LinearCRS
