@@ -391,6 +391,22 @@ def side_measurements(dev):
             out[f'gelu3_{tag}_{label}_GBps'] = nbytes / (statistics.median(ts) / 1e3) / 1e9
         del x, g, y, gin, state, flush
     out['note'] = '128x128x3072 elements, median of 20 launches, L2 flushed between launches'
+    # RandomizedLinear's projection (configs[4] shape: N = 16384 tokens, P = 3276 rows, D = 768),
+    # the one tensor-pipe kernel of the path: TFLOP/s = 2 P N D / time, against the measured bf16 peak.
+    tokens, rows, features = 16384, 3276, 768
+    x = torch.randn(tokens, features, device=dev).to(torch.bfloat16)
+    for kind in ('gaussian', 'rademacher'):
+        ts = []
+        for it in range(25):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); native.sketch_forward(x, rows, 1, it, kind, 1.0 / rows); b.record()
+            torch.cuda.synchronize()
+            if it >= 5:
+                ts.append(a.elapsed_time(b))
+        out[f'sketch_{kind}_D768_TFLOPs'] = 2.0 * rows * tokens * features / (statistics.median(ts) / 1e3) / 1e12
+    peaks = ROOT / 'MEASURED_PEAKS.json'
+    if peaks.exists():
+        out['sketch_peak_bf16_TFLOPs'] = json.loads(peaks.read_text()).get('bf16_tflops')
     return out
 
 
