@@ -407,6 +407,8 @@ def side_measurements(dev):
     peaks = ROOT / 'MEASURED_PEAKS.json'
     if peaks.exists():
         out['sketch_peak_bf16_TFLOPs'] = json.loads(peaks.read_text()).get('bf16_tflops')
+    out['sketch_note'] = ('one call at a time, synchronised, including the workspace allocation and the split-K '
+                          'reduce kernel; back to back: benchmarks/sketch_bench.py, profiles/r01_sketch_bench.json')
     return out
 
 
