@@ -25,7 +25,7 @@ import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
-PUBLISHED = {'gelu3': -13.8, 'rand0.2': -18.6, 'both': -32.7}   # reference README.md:18-27, percent
+PUBLISHED = {'gelu3': -13.8, 'rand0.2': -18.6, 'both': -32.7}   # reference README.md:18-27, percent; 'both-shared' = both + q/k/v share one sketch
 
 
 def build_model(variant: str, dtype):
@@ -38,17 +38,17 @@ def build_model(variant: str, dtype):
                            hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, num_labels=2)
     model = RobertaForSequenceClassification(config).to('cuda', dtype)
     swapped = {'gelu': 0, 'linear': 0}
-    if variant in ('gelu3', 'both'):
+    if variant in ('gelu3', 'both', 'both-shared'):
         def swap_gelu(module, path):
             if isinstance(module, (GELUActivation, torch.nn.GELU)):
                 swapped['gelu'] += 1
                 return fewbit.GELU(bits=3)
             return module
         model = fewbit.map_module(model, swap_gelu)
-    if variant in ('rand0.2', 'both'):
+    if variant in ('rand0.2', 'both', 'both-shared'):
         def swap_linear(module, path):     # benchmark/bench-linear.py:138-144
             out = fewbit.convert_linear(module, fewbit.RandomizedLinear, proj_dim_ratio=0.2,
-                                        proj_dim_min=3)
+                                        proj_dim_min=3, share_sketch=variant == 'both-shared')
             swapped['linear'] += out is not module
             return out
         model = fewbit.map_module(model, swap_linear)

@@ -15,6 +15,8 @@ i.e. the same ``S`` in every layer and step), and ``S`` is created in the input 
 """
 from __future__ import annotations
 
+import weakref
+
 from typing import Literal, Optional
 
 import torch as T
@@ -111,13 +113,28 @@ def _draw_stream(generator: T.Generator):
     return seed, offset
 
 
+class _SharedSketch:
+    """The last sketch taken with ``share_sketch=True``, per device: layers that are fed the very
+    same tensor one after the other (the query / key / value projections of an attention block)
+    reuse one ``S X`` instead of sketching it three times.  Only a weak reference
+    to the input is kept -- the point of the layer is NOT to keep its input alive."""
+    __slots__ = ('input', 'version', 'rows', 'kind', 'projection', 'stream')
+
+    def matches(self, tensor: T.Tensor, rows: int, kind: str) -> bool:
+        return (self.input() is tensor and self.version == tensor._version and self.rows == rows
+                and self.kind == kind)
+
+
+_SHARED: dict = {}
+
+
 class LinearGRPFunc(T.autograd.Function):
 
     @staticmethod
     def forward(ctx, input: T.Tensor, weight: T.Tensor, bias: Optional[T.Tensor],
                 proj_dim_ratio: Optional[float], proj_dim: Optional[int],
                 proj_dim_max: Optional[int], proj_dim_min: Optional[int], matmul: MatMulType,
-                generator: Optional[T.Generator]) -> T.Tensor:
+                generator: Optional[T.Generator], share_sketch: bool = False) -> T.Tensor:
         if proj_dim_ratio is None and proj_dim is None:
             raise ValueError('Either proj_dim or proj_dim_ratio should be specified.')
         if proj_dim_min and proj_dim_min <= 0:
@@ -132,9 +149,18 @@ class LinearGRPFunc(T.autograd.Function):
 
         if _native_sketch_available(input_view, matmul) and generator.device.type == 'cuda':
             # B200 path: S never exists in memory; (seed, offset) replaces the generator state.
-            seed, offset = _draw_stream(generator)
-            scale = 1.0 / proj_features if matmul == 'gaussian' else 4.0 / proj_features
-            input_proj = _native_sketch(input_view, proj_features, seed, offset, matmul, scale).to(input.dtype)
+            shared = _SHARED.get(input.device) if share_sketch else None
+            if shared is not None and shared.matches(input, proj_features, matmul):
+                input_proj, (seed, offset) = shared.projection, shared.stream
+            else:
+                seed, offset = _draw_stream(generator)
+                scale = 1.0 / proj_features if matmul == 'gaussian' else 4.0 / proj_features
+                input_proj = _native_sketch(input_view, proj_features, seed, offset, matmul, scale).to(input.dtype)
+                if share_sketch:
+                    shared = _SHARED[input.device] = _SharedSketch()
+                    shared.input, shared.version = weakref.ref(input), input._version
+                    shared.rows, shared.kind = proj_features, matmul
+                    shared.projection, shared.stream = input_proj, (seed, offset)
             ctx.save_for_backward(input_proj, weight, bias)
             ctx.proj_features = proj_features
             ctx.matmul = matmul
@@ -185,7 +211,7 @@ class LinearGRPFunc(T.autograd.Function):
             grad_weight = (proj @ grad_view).T @ input_proj
         if bias is not None and ctx.needs_input_grad[2]:
             grad_bias = grad_output.reshape(-1, grad_output.shape[-1]).sum(dim=0)
-        return (grad_input, grad_weight, grad_bias) + (None, ) * 6
+        return (grad_input, grad_weight, grad_bias) + (None, ) * 7
 
 
 linear_grp = LinearGRPFunc.apply

@@ -48,6 +48,10 @@ class LinearGRP(T.nn.Linear):
         proj_dim_min, proj_dim_max: clamp of the projection size.
         matmul: ``'gaussian'`` (default) or ``'rademacher'``.
         generator: random generator; default is the device's global generator.
+        share_sketch: (not in the reference) on CUDA, layers that are called one after the other
+            on the very same tensor -- query / key / value of an attention block -- share one
+            sketch ``S X`` instead of taking three: the same ``S`` then serves the three weight
+            gradients (each still unbiased, their noise correlated).  Default ``False``.
 
     Either ``proj_dim_ratio`` or ``proj_dim`` must be given.
 
@@ -62,9 +66,10 @@ class LinearGRP(T.nn.Linear):
                  dtype=None, proj_dim_ratio: Optional[float] = None,
                  proj_dim: Optional[int] = None, proj_dim_min: Optional[int] = None,
                  proj_dim_max: Optional[int] = None, matmul: MatMulType = 'gaussian',
-                 generator: Optional[T.Generator] = None) -> None:
+                 generator: Optional[T.Generator] = None, share_sketch: bool = False) -> None:
         super().__init__(in_features, out_features, bias, device, dtype)
         self.generator = generator
+        self.share_sketch = share_sketch
         self.matmul = matmul
         self.proj_dim_ratio = proj_dim_ratio
         self.proj_dim = proj_dim
@@ -73,7 +78,8 @@ class LinearGRP(T.nn.Linear):
 
     def forward(self, input: T.Tensor) -> T.Tensor:
         return linear_grp(input, self.weight, self.bias, self.proj_dim_ratio, self.proj_dim,
-                          self.proj_dim_max, self.proj_dim_min, self.matmul, self.generator)
+                          self.proj_dim_max, self.proj_dim_min, self.matmul, self.generator,
+                          self.share_sketch)
 
     def extra_repr(self) -> str:
         return ', '.join([

@@ -128,3 +128,45 @@ def test_randomized_linear_is_unbiased_on_cuda():
     z.backward(torch.ones_like(z))
     err = torch.linalg.norm(acc / 2048 - ref.weight.grad) / torch.linalg.norm(ref.weight.grad)
     assert err.item() < 0.1
+
+
+def test_layers_fed_the_same_tensor_can_share_one_sketch():
+    """share_sketch=True: query / key / value style layers called one after the other
+    on the very same tensor take ONE sketch -- one projection launch, one advance of the random
+    stream, one saved S X -- and each weight gradient is still (S G)^T (S X) with that S.  A different
+    tensor, or the same tensor modified in place, is sketched afresh."""
+    torch.manual_seed(5)
+    gen = torch.Generator(DEV).manual_seed(7)
+    q, k, v = (fewbit.RandomizedLinear(256, 128, proj_dim=64, generator=gen, share_sketch=True).to(DEV)
+               for _ in range(3))
+    hidden = torch.randn(4, 128, 256, device=DEV, requires_grad=True) * 1.0
+    grads = [torch.randn(4, 128, 128, device=DEV) for _ in range(3)]
+    seed, offset = gen.initial_seed(), gen.get_offset()
+    before = native.lib().fewbit_launch_count()
+    outs = [layer(hidden) for layer in (q, k, v)]
+    torch.cuda.synchronize()
+    launches = native.lib().fewbit_launch_count() - before
+    assert gen.get_offset() == offset + 4                         # one draw for the three layers
+    sum(o.mul(g).sum() for o, g in zip(outs, grads)).backward()
+    s = native.sketch_matrix(64, 512, seed, offset, 'gaussian', DEV).float()
+    xb = hidden.detach().reshape(512, 256).to(torch.bfloat16).float()
+    x_proj = (s @ xb) / 64
+    for layer, g in zip((q, k, v), grads):
+        want = (s @ g.reshape(512, 128).to(torch.bfloat16).float()).T @ x_proj
+        rel = (layer.weight.grad - want).norm() / want.norm()
+        assert rel.item() < 1e-3
+    # three forward sketches would be >= 3 projection launches; shared: one (+ its split-K reduce)
+    single = native.lib().fewbit_launch_count()
+    fewbit.RandomizedLinear(256, 128, proj_dim=64, generator=gen).to(DEV)(hidden.detach())
+    torch.cuda.synchronize()
+    per_sketch = native.lib().fewbit_launch_count() - single
+    assert launches == per_sketch, (launches, per_sketch)
+    # a modified or different tensor is not a hit
+    offset = gen.get_offset()
+    with torch.no_grad():
+        fresh = hidden.detach().clone()
+        q(fresh)
+        fresh.add_(1.0)
+        k(fresh)
+        v(fresh.clone())
+    assert gen.get_offset() == offset + 12
