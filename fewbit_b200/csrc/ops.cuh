@@ -420,6 +420,33 @@ template <class L> __device__ __forceinline__ L elu(L x, float pos, float neg, f
     return if_greater(x, lane<L>(0.0f), mul_(x, lane<L>(pos)),
                       mul_(expm1_nonpos(mul_(x, lane<L>(in_scale))), lane<L>(neg)));
 }
+// a / d for a finite d with 2^-120 < |d| < 2^120: MUFU.RCP, one Newton step, and the quotient's
+// residual folded back in -- the correctly rounded result in all but rare ties, six pairable
+// operations against the ~9 (plus a slow-path check) of the IEEE division sequence.
+template <class L> __device__ __forceinline__ L quotient(L a, L d) {
+    const L y0 = rcp_(d);
+    const L y = fma_(fma_(neg_(d), y0, lane<L>(1.0f)), y0, y0);
+    const L q = mul_(a, y);
+    return fma_(fma_(neg_(d), q, a), y, q);
+}
+// 1 + e^-x, with -x capped at 80 so that the denominator stays inside quotient()'s range; below
+// x = -80 the results differ from the exact ones by less than 2e-33 (NaN stays NaN).
+template <class L> __device__ __forceinline__ L one_plus_exp_neg(L x) {
+    const L z = neg_(x);
+    return add_(expf_(if_greater(z, lane<L>(80.0f), lane<L>(80.0f), z)), lane<L>(1.0f));
+}
+template <class L> __device__ __forceinline__ L sigmoid(L x) { return quotient(lane<L>(1.0f), one_plus_exp_neg(x)); }
+// x / (1 + e^-x).  An infinite numerator would turn the residual step into inf - inf: +inf stays
+// +inf and -inf gives NaN (-inf / inf), as ATen's and the reference's expression do.
+template <class L> __device__ __forceinline__ L silu(L x) {
+    const L special = if_greater(x, lane<L>(0.0f), x, lane<L>(CUDART_NAN_F));
+    return if_less(abs_(x), lane<L>(CUDART_INF_F), quotient(x, one_plus_exp_neg(x)), special);
+}
+// x n / (n + 2), n = e (e + 2), e = e^min(x, 20) <= 4.9e8: the denominator is at most 2.4e17
+template <class L> __device__ __forceinline__ L mish(L x) {
+    const L e = expf_(min_(x, lane<L>(20.0f))), n = mul_(e, add_(e, lane<L>(2.0f)));
+    return mul_(x, quotient(n, add_(n, lane<L>(2.0f))));
+}
 // min(0, x) - log1p(exp(-|x|)): ATen's own expression
 template <class L> __device__ __forceinline__ L logsigmoid(L x) {
     return add_(min_(x, lane<L>(0.0f)), neg_(log1p_unit(expf_(neg_(abs_(x))))));
@@ -520,26 +547,28 @@ struct MishFn {  // codec.cu:578-586
     __host__ MishFn(double, double) {}
     template <typename T> __device__ __forceinline__ float eval(float x) const {
         if constexpr (sizeof(T) == 2) return bf16_value(x);
-        const float e = expf(fminf(x, 20.0f)), n = e * (e + 2.0f);
-        return x * (n / (n + 2.0f));
+        return f32_value(x);
     }
     FEWBIT_BF16_FORMULA(true, fast::mish<float>(x), fast::mish<Pair>(x))
+    FEWBIT_F32_FORMULA(accurate::mish<float>(x), accurate::mish<Pair>(x))
 };
 struct SigmoidFn {  // codec.cu:602-607
     __host__ SigmoidFn(double, double) {}
     template <typename T> __device__ __forceinline__ float eval(float x) const {
         if constexpr (sizeof(T) == 2) return bf16_value(x);
-        return 1.0f / (1.0f + expf(-x));
+        return f32_value(x);
     }
     FEWBIT_BF16_FORMULA(true, fast::sigmoid<float>(x), fast::sigmoid<Pair>(x))
+    FEWBIT_F32_FORMULA(accurate::sigmoid<float>(x), accurate::sigmoid<Pair>(x))
 };
 struct SiluFn {  // codec.cu:609-614
     __host__ SiluFn(double, double) {}
     template <typename T> __device__ __forceinline__ float eval(float x) const {
         if constexpr (sizeof(T) == 2) return bf16_value(x);
-        return x / (1.0f + expf(-x));
+        return f32_value(x);
     }
     FEWBIT_BF16_FORMULA(true, fast::silu<float>(x), fast::silu<Pair>(x))
+    FEWBIT_F32_FORMULA(accurate::silu<float>(x), accurate::silu<Pair>(x))
 };
 struct SoftplusFn {  // codec.cu:616-632
     float beta, threshold, inv_beta;
@@ -622,7 +651,7 @@ FEWBIT_TILE_HINT_F32(TanhFn, 2, 3)
 FEWBIT_TILE_HINT_F32(TanhshrinkFn, 2, 3)
 FEWBIT_TILE_HINT_F32(SigmoidFn, 2, 3)
 FEWBIT_TILE_HINT_F32(MishFn, 2, 3)
-FEWBIT_TILE_HINT_F32(SiluFn, 2, 4)
+FEWBIT_TILE_HINT_F32(SiluFn, 2, 3)
 FEWBIT_TILE_HINT_F32(SoftplusFn, 2, 4)
 #undef FEWBIT_TILE_HINT_F32
 

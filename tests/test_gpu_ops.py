@@ -110,9 +110,10 @@ def test_bf16_results_are_the_fp32_exact_rounding(name):
 
 
 @pytest.mark.parametrize('name,bound', [('elu', 1.5), ('celu', 1.5), ('selu', 2.5), ('logsigmoid', 3.5),
-                                        ('softplus', 3.5)])
+                                        ('softplus', 3.5), ('sigmoid', 3.5), ('silu', 3.5), ('mish', 5.0)])
 def test_fp32_own_expm1_and_log1p_against_float64(name, bound):
-    """The fp32 ELU family, logsigmoid and softplus use own expm1 / log1p code instead of libdevice
+    """The fp32 ELU family, logsigmoid and softplus use own expm1 / log1p code instead of libdevice,
+    sigmoid / silu / mish an own correctly rounded quotient instead of the IEEE division sequence
     (ops.cuh namespace accurate; tools/fit_fp32_math.py).  Against float64 on wide inputs --
     N(0, 2^2), N(0, 20^2), a dense sweep of [-100, 100], signed zeros, tiny and huge values, the
     exponent-range edges, NaN and infinities -- they stay within `bound` ulp (measured: 0.87, 0.87,
@@ -127,13 +128,16 @@ def test_fp32_own_expm1_and_log1p_against_float64(name, bound):
     aten = getattr(F, name)(x)
     exact = getattr(F, name)(x.double())
     assert torch.equal(torch.isnan(y), torch.isnan(aten)) and torch.equal(torch.isinf(y), torch.isinf(aten))
-    finite = torch.isfinite(exact)
+    # results at the bottom of the exponent range (sigmoid / silu below x = -80) are compared absolutely
+    tiny = torch.isfinite(exact) & (exact.abs() < 1e-30)
+    assert (y.double() - exact).abs()[tiny].max().item() < 1e-30 if tiny.any() else True
+    finite = torch.isfinite(exact) & ~tiny
     mag = exact.float().abs()
     ulp = (torch.nextafter(mag, torch.full_like(mag, float('inf'))) - mag).double()
     ours = ((y.double() - exact).abs() / ulp)[finite].max().item()
     apart = ((y.double() - aten.double()).abs() / ulp)[finite].max().item()
     assert ours <= bound, f'{name}: {ours:.2f} ulp from float64'
-    assert apart <= 3.0, f'{name}: {apart:.2f} ulp from ATen'
+    assert apart <= (5.0 if name == 'mish' else 3.0), f'{name}: {apart:.2f} ulp from ATen'
 
 
 @pytest.mark.parametrize('name', ['gelu', 'selu', 'softsign', 'hardswish'])
