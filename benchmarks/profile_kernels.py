@@ -45,4 +45,17 @@ if which in ('all', 'sketch'):
     for _ in range(reps):
         native.sketch_forward(x, 3276, 1, 0, 'gaussian', 1.0 / 3276)
     torch.cuda.synchronize()
+
+if which == 'r2fwd':
+    # the forward kernels VERDICT r1 asks ncu rows for: gelu bf16 3 / 7 bits, hardswish bf16 7 bits (+ gelu 5, 8)
+    from fewbit_b200.functional import store as _store
+    n = 128 * 128 * 3072
+    x = (torch.randn(n, device=dev) * 2).to(torch.bfloat16)
+    y = torch.empty_like(x)
+    for name, bits in (('gelu', 3), ('gelu', 7), ('hardswish', 7), ('gelu', 5), ('gelu', 8), ('tanh', 3)):
+        borders, _ = _store.get(name, bits, dev, torch.bfloat16)
+        state = native.new_state(x, bits)
+        for _ in range(reps):
+            native.stepwise_forward(name, x, y, state, bits, borders[1:-1].contiguous())
+        torch.cuda.synchronize()
 print('done')

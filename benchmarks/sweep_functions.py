@@ -12,7 +12,7 @@ rank's fraction of peak.
 
 GB/s = algorithmic bytes n (s + s + b/8) / CUDA-event time (12 back-to-back launches over four
 rotating buffer sets so nothing is served from L2, median of 5 rounds).  Bits 1-4 use the
-built-in tables, 5-8 `make_table`.
+built-in tables, 5-8 the shipped optimal tables (`--tables synthetic`: `make_table`).
 """
 from __future__ import annotations
 
@@ -85,6 +85,8 @@ def main():
     ap.add_argument('--dtypes', default='f32,bf16')
     ap.add_argument('--json', default=None)
     ap.add_argument('--md', default=None)
+    ap.add_argument('--tables', default='shipped', choices=('shipped', 'synthetic'),
+                    help='bits 5-8: the tables the package ships (data/extended.npz) or make_table() quantile grids')
     args = ap.parse_args()
     bits_list = [int(b) for b in args.bits.split(',')]
     only = set(args.functions.split(',')) if args.functions else None
@@ -119,7 +121,7 @@ def main():
             if only and name not in only:
                 continue
             for bits in bits_list:
-                if bits <= 4:
+                if bits <= 4 or args.tables == 'shipped':
                     borders, levels = store.get(name, bits, dev, dtype)
                 else:
                     borders, levels = (t.to(dev, dtype) for t in make_table(name, bits))

@@ -7,6 +7,12 @@
 
 #include "tile.cuh"
 
+// The bucket search below computes table indices as the bit patterns of denormal floats; with
+// flush-to-zero every look-up would silently hit entry 0.
+#ifdef __CUDA_FTZ
+#error "fewbit_b200 must be compiled without -ftz=true / --use_fast_math (denormal arithmetic is load-bearing)"
+#endif
+
 namespace fewbit {
 
 struct NoScratch {
@@ -46,7 +52,10 @@ template <typename T, int B> struct Bucketizer<T, B, true> {
             b[i] = i < nbounds ? to_float<T>(bounds[i]) : CUDART_INF_F;
     }
 
-    __device__ __forceinline__ void lookup(const float (&x)[8], uint32_t (&code)[8]) const {
+    static constexpr bool kMayCrowd = false;
+    template <bool>
+    __device__ __forceinline__ void lookup(const Scratch &, const float (&x)[8], uint32_t (&half)[2]) const {
+        uint32_t code[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if constexpr (B == 1) {
@@ -57,61 +66,31 @@ template <typename T, int B> struct Bucketizer<T, B, true> {
                 code[j] = (p1 ? 2u : 0u) | (p2 ? 1u : 0u);
             }
         }
+        half[0] = pack4<B>(code[0], code[1], code[2], code[3]);
+        half[1] = pack4<B>(code[4], code[5], code[6], code[7]);
     }
 };
 
-__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
-    uint32_t v;
-    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
-    uint32_t v;
-    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-    float v;
-    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
+// acc += kInc if a < b: one FSETP and one predicated add (left to the compiler the same
+// expression became an add, a compare and a predicated move).
+template <uint32_t kInc> __device__ __forceinline__ void add_if_less(uint32_t &acc, float a, float b) {
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p add.u32 %0, %0, %3;\n\t}"
+        : "+r"(acc) : "f"(a), "f"(b), "n"(kInc));
 }
 
-#ifndef FEWBIT_ADDR_PAIRS
-#define FEWBIT_ADDR_PAIRS 1
-#endif
 __device__ __forceinline__ unsigned long long pack2(float v) {
     unsigned long long r;
     asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v));
     return r;
 }
 
-template <typename T, int B> struct Bucketizer<T, B, false> {
-    static constexpr int kSize = 1 << B;  // bounds padded with +inf to a power of two
-    // Cells: enough to separate the borders of every shipped table, few enough that the
-    // gather stays (nearly) bank-conflict free: 128 one-byte entries = 32 words = 1 per bank.
-    static constexpr int kCells = B == 3 ? 128 : B == 4 ? 256 : B == 5 ? 512 : 2048;
-    struct Scratch {
-        float bounds[kSize];
-        uint16_t bound_cell[kSize];
-        alignas(4) uint8_t lut[kCells];
-    };
-    const T *bounds;
-    int nbounds;
+// Cell index of x: sat() clamps (and sends NaN to 0); the multiply works in the denormal range,
+// where the bit pattern of a float *is* its value in units of 2^-149, so the bits of the product
+// are round(t * (C-1)) -- an integer straight off the FMA pipe, no conversion instruction.
+// (Needs denormals: the build refuses -ftz=true / --use_fast_math, see the #error above.)
+struct CellMap {
     float scale, offset;
-    float lut_base;       // shared-space byte address of lut[], as the bits of a denormal float
-    uint32_t table_base;  // shared-space byte address of bounds[]
-    const float *table;
-    bool crowded;         // some cell holds >= 2 borders: the whole block searches exactly
-
-    // Shared-memory address of x's LUT entry, computed entirely on the FMA pipe: sat() clamps
-    // (and sends NaN to 0); the second FMA works in the denormal range, where the bit pattern
-    // of a float *is* its value in units of 2^-149, so  bits = round(t * (C-1)) + base.
-    __device__ __forceinline__ uint32_t entry_address(float x) const {
-        const float t = __saturatef(fmaf(x, scale, offset));
-        return __float_as_uint(fmaf(t, __uint_as_float((uint32_t)(kCells - 1)), lut_base));
-    }
-
-    __device__ __forceinline__ void prepare(Scratch &s) {
+    template <typename T> __device__ __forceinline__ void fit(const T *bounds, int nbounds) {
         const float lo = nbounds > 0 ? to_float<T>(bounds[0]) : 0.0f;
         const float hi = nbounds > 0 ? to_float<T>(bounds[nbounds - 1]) : 0.0f;
         const float span = hi - lo;
@@ -123,67 +102,159 @@ template <typename T, int B> struct Bucketizer<T, B, false> {
             offset = 0.5f - lo;
         }
         if (!(fabsf(offset) < CUDART_INF_F)) offset = 0.5f;
-        const uint32_t lut_address = (uint32_t)__cvta_generic_to_shared(s.lut);
-        lut_base = __uint_as_float(lut_address);
-        table_base = (uint32_t)__cvta_generic_to_shared(s.bounds);
-        table = s.bounds;
-        for (int i = threadIdx.x; i < kSize; i += blockDim.x) {
-            const float v = i < nbounds ? to_float<T>(bounds[i]) : CUDART_INF_F;
-            s.bounds[i] = v;
-            s.bound_cell[i] = i < nbounds ? (uint16_t)(entry_address(v) - lut_address) : (uint16_t)kCells;
-        }
-        __syncthreads();
-        int shared_cell = 0;
-        for (int c = threadIdx.x; c < kCells; c += blockDim.x) {
-            int k = 0;  // first bound whose cell is >= c
-#pragma unroll
-            for (int step = kSize >> 1; step >= 1; step >>= 1)
-                if (s.bound_cell[k + step - 1] < c) k += step;
-            shared_cell |= (k + 1 < kSize && s.bound_cell[k + 1] == c) ? 1 : 0;
-            s.lut[c] = (uint8_t)k;
-        }
-        crowded = __syncthreads_or(shared_cell) != 0;
     }
+    template <int kCells> __device__ __forceinline__ uint32_t cell(float x) const {
+        const float t = __saturatef(fmaf(x, scale, offset));
+        return __float_as_uint(__fmul_rn(t, __uint_as_float((uint32_t)(kCells - 1))));
+    }
+    // two elements per multiply (mul.rn.f32x2): the clamp has no packed form, the product does
+    template <int kCells>
+    __device__ __forceinline__ void cells(float x0, float x1, uint32_t &c0, uint32_t &c1) const {
+        const float t0 = __saturatef(fmaf(x0, scale, offset));
+        const float t1 = __saturatef(fmaf(x1, scale, offset));
+        unsigned long long t2, a2;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(t2) : "f"(t0), "f"(t1));
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(a2) : "l"(t2), "l"(pack2(__uint_as_float((uint32_t)(kCells - 1)))));
+        asm("mov.b64 {%0, %1}, %2;" : "=r"(c0), "=r"(c1) : "l"(a2));
+    }
+};
 
-    // Exact branch-free binary search; out of line on purpose (rare, keeps the hot loop small).
-    static __device__ __noinline__ uint32_t exact(const float *sorted, float x) {
-        int k = 0;
+// Exact branch-free binary search over `kSize - 1` sorted borders padded with +inf; out of line
+// on purpose (rare: only tables whose borders the cells cannot separate; keeps the hot loop small).
+// The table is named by its shared-space address: handing a generic pointer to an out-of-line
+// function makes the compiler address ALL of the kernel's shared memory through a window base
+// register (one extra add per look-up in the hot loop).
+template <int kSize> __device__ __noinline__ uint32_t search_exact(uint32_t sorted, float x) {
+    uint32_t k = 0;
+    for (int step = kSize >> 1; step >= 1; step >>= 1) {
+        float v;
+        asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sorted + 4u * (k + step - 1)));
+        if (v < x) k += step;
+    }
+    return k;
+}
+
+// Borders -> cells, shared by both table layouts: fills s.bounds / s.bound_cell, then calls
+// `emit(cell, k, has_border)` for every cell with k = #{borders in earlier cells}; returns
+// (block-wide) whether some cell holds two or more borders.
+template <int kSize, int kCells, typename T, class Scratch, class Emit>
+__device__ __forceinline__ bool build_cells(const CellMap &map, const T *bounds, int nbounds, Scratch &s,
+                                            Emit emit) {
+    for (int i = threadIdx.x; i < kSize; i += blockDim.x) {
+        const float v = i < nbounds ? to_float<T>(bounds[i]) : CUDART_INF_F;
+        s.bounds[i] = v;
+        s.bound_cell[i] = i < nbounds ? (uint16_t)map.cell<kCells>(v) : (uint16_t)kCells;
+    }
+    __syncthreads();
+    int shared_cell = 0;
+    for (int c = threadIdx.x; c < kCells; c += blockDim.x) {
+        int k = 0;  // first border whose cell is >= c
 #pragma unroll
         for (int step = kSize >> 1; step >= 1; step >>= 1)
-            if (sorted[k + step - 1] < x) k += step;
-        return (uint32_t)k;
+            if (s.bound_cell[k + step - 1] < c) k += step;
+        shared_cell |= (k + 1 < kSize && s.bound_cell[k + 1] == c) ? 1 : 0;
+        emit(c, k, k < kSize && s.bound_cell[k] == c);
     }
+    return __syncthreads_or(shared_cell) != 0;
+}
 
-    __device__ __forceinline__ void lookup(const float (&x)[8], uint32_t (&code)[8]) const {
-        if (crowded) {  // block-uniform
-#pragma unroll
-            for (int j = 0; j < 8; ++j) code[j] = exact(table, x[j]);
-            return;
+// Two layouts behind one interface; which one serves (T, B) is decided by kOneGather below.
+//
+// fp32 -- two gathers: a byte per cell holding 4k (k at 7 and 8 bits, where 4k does not fit) and
+// the borders themselves; code = k + (bounds[k] < x).  128 one-byte cells are 32 words, one per
+// bank, and the 8 borders of a 3-bit table sit in 8 different banks: at 3 bits neither gather has
+// a bank conflict.  The four k of a half are packed before the comparison results are added in, so
+// a code costs one multiply-add and one predicated add.
+//
+// bf16 -- one gather: a 32-bit word per cell.  Borders of a bf16 table are bf16 values, so the low
+// 16 bits of a border's float pattern are free.  The word is built so that, read as a float, it
+// lies in [border, next bf16 above border) -- no bf16 input falls strictly inside, so
+// (word < x) == (border < x) for every bf16 x -- while its low 16 bits carry k = #{borders in
+// earlier cells}, replicated at every position a code can take inside a packed half (B <= 4: four
+// copies, at bits 0, B, 2B, 3B; wider codes: two copies, the half is assembled from two pairs).
+// Packing the k of element j is then ONE logic op, acc |= word & (mask << B j), and the code is
+// completed by a predicated add of 1 << B j.  Cells without a border hold +inf or a NaN pattern
+// (never below x).
+template <typename T, int B> struct Bucketizer<T, B, false> {
+    static constexpr bool kOneGather = sizeof(T) == 2;
+    static constexpr int kSize = 1 << B;  // borders padded with +inf to a power of two
+    static constexpr int kCells = kOneGather ? (16 << B) : B == 3 ? 128 : B == 4 ? 256 : B == 5 ? 512 : 2048;
+    static constexpr int kShift = B <= 6 ? 2 : 0;   // byte entries hold k << kShift
+    static constexpr int kCopies = B <= 4 ? 4 : 2;
+    struct Scratch {
+        float bounds[kSize];
+        uint16_t bound_cell[kSize];
+        alignas(4) uint8_t lut[kOneGather ? 4 : kCells];
+        uint32_t word[kOneGather ? kCells : 1];
+    };
+    const T *bounds;
+    int nbounds;
+    CellMap map;
+    bool crowded;  // some cell holds >= 2 borders: the whole block searches exactly
+
+    static __device__ __forceinline__ uint32_t encode(float border, uint32_t k) {
+        uint32_t low = k | (k << B);
+        if (kCopies == 4) low |= low << (2 * B);
+        const uint32_t bits = __float_as_uint(border);
+        if ((bits << 1) == 0) return low;           // +-0: a denormal below every positive bf16
+        // negative borders: the values of (border, next bf16 towards zero) have the next bf16's
+        // high half; with nothing to carry the border itself will do
+        if ((bits >> 31) && low != 0) return (bits - 0x10000u) | low;
+        return bits | low;                          // (+inf: a NaN pattern unless k == 0)
+    }
+    __device__ __forceinline__ void prepare(Scratch &s) {
+        map.fit(bounds, nbounds);
+        crowded = build_cells<kSize, kCells>(map, bounds, nbounds, s, [&](int c, int k, bool has) {
+            if constexpr (kOneGather)
+                s.word[c] = encode(has ? s.bounds[k] : CUDART_INF_F, (uint32_t)k);
+            else
+                s.lut[c] = (uint8_t)(k << kShift);
+        });
+    }
+    __device__ __forceinline__ uint32_t half(const Scratch &s, float x0, float x1, float x2, float x3) const {
+        uint32_t c0, c1, c2, c3;
+        map.cells<kCells>(x0, x1, c0, c1);
+        map.cells<kCells>(x2, x3, c2, c3);
+        uint32_t acc;
+        float b0, b1, b2, b3;
+        if constexpr (kOneGather) {
+            const uint32_t w0 = s.word[c0], w1 = s.word[c1], w2 = s.word[c2], w3 = s.word[c3];
+            constexpr uint32_t m = (1u << B) - 1u;
+            if constexpr (kCopies == 4) {
+                acc = (w0 & m) | (w1 & (m << B)) | (w2 & (m << (2 * B))) | (w3 & (m << (3 * B)));
+            } else {
+                acc = ((w0 & m) | (w1 & (m << B))) + (((w2 & m) | (w3 & (m << B))) << (2 * B));
+            }
+            b0 = __uint_as_float(w0), b1 = __uint_as_float(w1), b2 = __uint_as_float(w2), b3 = __uint_as_float(w3);
+        } else {
+            const uint32_t e0 = s.lut[c0], e1 = s.lut[c1], e2 = s.lut[c2], e3 = s.lut[c3];
+            const char *table = reinterpret_cast<const char *>(s.bounds);
+            b0 = *reinterpret_cast<const float *>(table + (e0 << (2 - kShift)));
+            b1 = *reinterpret_cast<const float *>(table + (e1 << (2 - kShift)));
+            b2 = *reinterpret_cast<const float *>(table + (e2 << (2 - kShift)));
+            b3 = *reinterpret_cast<const float *>(table + (e3 << (2 - kShift)));
+            acc = pack4<B>(e0, e1, e2, e3) >> kShift;
         }
-#if !FEWBIT_ADDR_PAIRS
+        add_if_less<1u>(acc, b0, x0);
+        add_if_less<1u << B>(acc, b1, x1);
+        add_if_less<1u << (2 * B)>(acc, b2, x2);
+        add_if_less<1u << (3 * B)>(acc, b3, x3);
+        return acc;
+    }
+    static constexpr bool kMayCrowd = true;
+    template <bool kExact>
+    __device__ __forceinline__ void lookup(const Scratch &s, const float (&x)[8], uint32_t (&out)[2]) const {
+        if constexpr (kExact) {
+            uint32_t code[8];
+            const uint32_t sorted = (uint32_t)__cvta_generic_to_shared(s.bounds);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) code[j] = lds_u8(entry_address(x[j]));
-#else
-        // entry_address() for two elements at a time: the clamp has no packed form, the
-        // denormal-range FMA does (see Pair below).
-        const unsigned long long cells2 = pack2(__uint_as_float((uint32_t)(kCells - 1)));
-        const unsigned long long base2 = pack2(lut_base);
-#pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-            const float t0 = __saturatef(fmaf(x[j], scale, offset));
-            const float t1 = __saturatef(fmaf(x[j + 1], scale, offset));
-            unsigned long long t2, a2;
-            uint32_t a0, a1;
-            asm("mov.b64 %0, {%1, %2};" : "=l"(t2) : "f"(t0), "f"(t1));
-            asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(a2) : "l"(t2), "l"(cells2), "l"(base2));
-            asm("mov.b64 {%0, %1}, %2;" : "=r"(a0), "=r"(a1) : "l"(a2));
-            code[j] = lds_u8(a0);
-            code[j + 1] = lds_u8(a1);
+            for (int j = 0; j < 8; ++j) code[j] = search_exact<kSize>(sorted, x[j]);
+            out[0] = pack4<B>(code[0], code[1], code[2], code[3]);
+            out[1] = pack4<B>(code[4], code[5], code[6], code[7]);
+        } else {
+            out[0] = half(s, x[0], x[1], x[2], x[3]);
+            out[1] = half(s, x[4], x[5], x[6], x[7]);
         }
-#endif
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (lds_f32(table_base + 4 * code[j]) < x[j]) code[j] += 1;
     }
 };
 
@@ -663,8 +734,13 @@ template <class Fn, typename T, int B> struct QuantizeOp {
     Fn fn;
     Bucketizer<T, B> bucket;
     __device__ __forceinline__ void prepare(Scratch &s) { bucket.prepare(s); }
-    __device__ __forceinline__ void apply(float (&v)[8], uint32_t (&code)[8]) const {
-        bucket.lookup(v, code);
+    __device__ __forceinline__ bool exact() const {
+        if constexpr (Bucketizer<T, B>::kMayCrowd) return bucket.crowded;
+        return false;
+    }
+    template <bool kExact>
+    __device__ __forceinline__ void apply(const Scratch &s, float (&v)[8], uint32_t (&half)[2]) const {
+        bucket.template lookup<kExact>(s, v, half);
         if constexpr (sizeof(T) == 2 && has_pairs<Fn>::value && FEWBIT_PAIRS) {
 #pragma unroll
             for (int j = 0; j < 8; j += 2) fn.bf16_pair(v[j], v[j + 1]);
@@ -784,9 +860,14 @@ template <class Fn> struct MaskOp {
     using Scratch = NoScratch;
     Fn fn;
     __device__ __forceinline__ void prepare(Scratch &) {}
-    __device__ __forceinline__ void apply(float (&v)[8], uint32_t (&code)[8]) const {
+    __device__ __forceinline__ bool exact() const { return false; }
+    template <bool>
+    __device__ __forceinline__ void apply(const Scratch &, float (&v)[8], uint32_t (&half)[2]) const {
+        uint32_t code[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = fn(v[j], code[j]);
+        half[0] = pack4<1>(code[0], code[1], code[2], code[3]);
+        half[1] = pack4<1>(code[4], code[5], code[6], code[7]);
     }
 };
 

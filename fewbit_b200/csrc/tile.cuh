@@ -89,6 +89,7 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(f
 template <typename T> struct Subtile;
 
 template <> struct Subtile<float> {
+    static constexpr int kVectors = 64;   // 128-bit vectors per subtile
     static __device__ __forceinline__ void load(const float *base, int lane, float (&v)[8]) {
         const uint4 *p = reinterpret_cast<const uint4 *>(base);
         uint4 a = ldg_stream(p + lane), b = ldg_stream(p + 32 + lane);
@@ -96,6 +97,20 @@ template <> struct Subtile<float> {
         v[2] = __uint_as_float(a.z), v[3] = __uint_as_float(a.w);
         v[4] = __uint_as_float(b.x), v[5] = __uint_as_float(b.y);
         v[6] = __uint_as_float(b.z), v[7] = __uint_as_float(b.w);
+    }
+    // the same through this lane's pointer (first vector of the subtile + lane)
+    static __device__ __forceinline__ void load_at(const uint4 *p, float (&v)[8]) {
+        uint4 a = ldg_stream(p), b = ldg_stream(p + 32);
+        v[0] = __uint_as_float(a.x), v[1] = __uint_as_float(a.y);
+        v[2] = __uint_as_float(a.z), v[3] = __uint_as_float(a.w);
+        v[4] = __uint_as_float(b.x), v[5] = __uint_as_float(b.y);
+        v[6] = __uint_as_float(b.z), v[7] = __uint_as_float(b.w);
+    }
+    static __device__ __forceinline__ void store_at(uint4 *p, const float (&v)[8]) {
+        stg_stream(p, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]),
+                                 __float_as_uint(v[2]), __float_as_uint(v[3])));
+        stg_stream(p + 32, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]),
+                                      __float_as_uint(v[6]), __float_as_uint(v[7])));
     }
     static __device__ __forceinline__ void store(float *base, int lane, const float (&v)[8]) {
         uint4 *p = reinterpret_cast<uint4 *>(base);
@@ -107,11 +122,21 @@ template <> struct Subtile<float> {
 };
 
 template <> struct Subtile<__nv_bfloat16> {
+    static constexpr int kVectors = 32;
     static __device__ __forceinline__ void load(const __nv_bfloat16 *base, int lane,
                                                 float (&v)[8]) {
         uint4 a = ldg_stream(reinterpret_cast<const uint4 *>(base) + lane);
         v[0] = bf16_lo(a.x), v[1] = bf16_hi(a.x), v[2] = bf16_lo(a.y), v[3] = bf16_hi(a.y);
         v[4] = bf16_lo(a.z), v[5] = bf16_hi(a.z), v[6] = bf16_lo(a.w), v[7] = bf16_hi(a.w);
+    }
+    static __device__ __forceinline__ void load_at(const uint4 *p, float (&v)[8]) {
+        uint4 a = ldg_stream(p);
+        v[0] = bf16_lo(a.x), v[1] = bf16_hi(a.x), v[2] = bf16_lo(a.y), v[3] = bf16_hi(a.y);
+        v[4] = bf16_lo(a.z), v[5] = bf16_hi(a.z), v[6] = bf16_lo(a.w), v[7] = bf16_hi(a.w);
+    }
+    static __device__ __forceinline__ void store_at(uint4 *p, const float (&v)[8]) {
+        stg_stream(p, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                 pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
     }
     static __device__ __forceinline__ void store(__nv_bfloat16 *base, int lane,
                                                  const float (&v)[8]) {
@@ -126,24 +151,6 @@ template <> struct Subtile<__nv_bfloat16> {
 // Bytes of packed state per subtile / per warp tile.
 template <int B> constexpr int subtile_bytes() { return 32 * B; }
 
-// Write the low B bytes of `octet` to the (B-byte aligned) shared-memory address `p`.
-template <int B> __device__ __forceinline__ void put_octet(uint8_t *p, uint64_t octet) {
-    if constexpr (B == 8) {
-        *reinterpret_cast<uint2 *>(p) = make_uint2((uint32_t)octet, (uint32_t)(octet >> 32));
-    } else if constexpr (B == 4) {
-        *reinterpret_cast<uint32_t *>(p) = (uint32_t)octet;
-    } else if constexpr (B % 2 == 0) {
-#pragma unroll
-        for (int k = 0; k < B / 2; ++k)
-            reinterpret_cast<uint16_t *>(p)[k] = (uint16_t)(octet >> (16 * k));
-    } else {
-#pragma unroll
-        for (int k = 0; k < B; ++k) p[k] = (uint8_t)(octet >> (8 * k));
-    }
-}
-
-// Forward: turn this lane's 8 codes of one subtile into its octet and park it in the strip.
-//   code[j] belongs to v[j] of Subtile<T>.
 // Four codes -> one 4*B-bit field.  Written as multiply-adds so that the shifts can go to the
 // FMA pipe (IMAD) instead of the ALU pipe, which is the busy one in the forward kernels.
 template <int B>
@@ -151,28 +158,152 @@ __device__ __forceinline__ uint32_t pack4(uint32_t c0, uint32_t c1, uint32_t c2,
     return c0 + c1 * (1u << B) + c2 * (1u << (2 * B)) + c3 * (1u << (3 * B));
 }
 
+// A forward op hands over the codes of its 8 values as two 4*B-bit halves (values 0..3, 4..7).
+// This lane's octet (B bytes, stream order) and its index 0..31 within the subtile:
+//   bf16: the lane's 8 values are octet `lane`.
+//   fp32: values [4l, 4l+4) are half (l & 1) of octet l >> 1, values [128+4l, 128+4l+4) are half
+//         (l & 1) of octet 16 + (l >> 1).  Even lanes assemble octet l >> 1 (they need the odd
+//         neighbour's first half), odd lanes octet 16 + (l >> 1) (the even neighbour's second
+//         half): one shuffle.
 template <typename T, int B>
-__device__ __forceinline__ void stage_codes(uint8_t *strip, int lane, const uint32_t (&code)[8]) {
-    const uint32_t first = pack4<B>(code[0], code[1], code[2], code[3]);
-    const uint32_t second = pack4<B>(code[4], code[5], code[6], code[7]);
-    if constexpr (sizeof(T) == 2) {
-        // bf16: the lane's 8 values are one octet.
-        const uint64_t octet = B <= 4 ? (uint64_t)(first | (second << ((4 * B) & 31)))
-                                      : ((uint64_t)first | ((uint64_t)second << (4 * B)));
-        put_octet<B>(strip + B * lane, octet);
-    } else {
-        // fp32: elements [4l, 4l+4) are half (l & 1) of octet l >> 1, elements
-        // [128+4l, 128+4l+4) are half (l & 1) of octet 16 + (l >> 1).  Even lanes assemble
-        // octet l>>1 (they need the odd neighbour's `first`), odd lanes assemble octet
-        // 16 + (l>>1) (they need the even neighbour's `second`): one shuffle.
+__device__ __forceinline__ uint64_t lane_octet(int lane, uint32_t first, uint32_t second) {
+    uint32_t low = first, high = second;
+    if constexpr (sizeof(T) == 4) {
         const bool odd = lane & 1;
         const uint32_t theirs = __shfl_xor_sync(0xffffffffu, odd ? first : second, 1);
-        const uint32_t low = odd ? theirs : first, high = odd ? second : theirs;
-        const uint64_t octet = B <= 4 ? (uint64_t)(low | (high << ((4 * B) & 31)))
-                                      : ((uint64_t)low | ((uint64_t)high << (4 * B)));
-        put_octet<B>(strip + B * ((lane >> 1) + (odd ? 16 : 0)), octet);
+        low = odd ? theirs : first, high = odd ? second : theirs;
+    }
+    if constexpr (B <= 4) return (uint64_t)(low | (high << ((4 * B) & 31)));
+    return (uint64_t)low | ((uint64_t)high << (4 * B));
+}
+template <typename T> __device__ __forceinline__ int octet_index(int lane) {
+    return sizeof(T) == 2 ? lane : (lane >> 1) + ((lane & 1) ? 16 : 0);
+}
+
+// Shared-memory accesses of the staging code name their location as a 32-bit shared-space address
+// plus a compile-time offset, so that every access is one instruction with an immediate offset off
+// a register that is set up once per kernel (left to pointer arithmetic the compiler recomputed
+// warp, lane and strip addresses for every subtile: ~12 of ~170 instructions).
+template <int kOffset> __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u8 [%0+%2], %1;" ::"r"(a), "r"(v), "n"(kOffset) : "memory");
+}
+template <int kOffset> __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u16 [%0+%2], %1;" ::"r"(a), "r"(v), "n"(kOffset) : "memory");
+}
+template <int kOffset> __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(a), "r"(v), "n"(kOffset) : "memory");
+}
+template <int kOffset> __device__ __forceinline__ void sts64(uint32_t a, uint32_t lo, uint32_t hi) {
+    asm volatile("st.shared.v2.u32 [%0+%3], {%1, %2};" ::"r"(a), "r"(lo), "r"(hi), "n"(kOffset) : "memory");
+}
+template <int kOffset> __device__ __forceinline__ uint64_t lds64(uint32_t a) {
+    uint32_t lo, hi;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(lo), "=r"(hi) : "r"(a), "n"(kOffset) : "memory");
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+template <int kOffset> __device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a), "n"(kOffset) : "memory");
+    return r;
+}
+
+// Write the low B bytes of `octet` to the (B-byte aligned) shared-memory address a + kOffset.
+template <int B, int kOffset> __device__ __forceinline__ void put_octet(uint32_t a, uint64_t octet) {
+    const uint32_t lo = (uint32_t)octet, hi = (uint32_t)(octet >> 32);
+    if constexpr (B == 8) {
+        sts64<kOffset>(a, lo, hi);
+    } else if constexpr (B == 4) {
+        sts32<kOffset>(a, lo);
+    } else if constexpr (B == 2) {
+        sts16<kOffset>(a, lo);
+    } else if constexpr (B == 6) {
+        sts16<kOffset>(a, lo), sts16<kOffset + 2>(a, lo >> 16), sts16<kOffset + 4>(a, hi);
+    } else {   // 1, 3, 5, 7
+        sts8<kOffset>(a, lo);
+        if constexpr (B >= 3) sts8<kOffset + 1>(a, lo >> 8), sts8<kOffset + 2>(a, lo >> 16);
+        if constexpr (B >= 5) sts8<kOffset + 3>(a, lo >> 24), sts8<kOffset + 4>(a, hi);
+        if constexpr (B >= 7) sts8<kOffset + 5>(a, hi >> 8), sts8<kOffset + 6>(a, hi >> 16);
     }
 }
+
+// Staging of the packed bytes of one warp tile (U subtiles) on their way to global memory.
+//
+// Direct (B = 1, 2, 3, 4, 8, or any tile that is not four subtiles): every lane drops its octet at
+// its stream position in the strip -- one store for B = 1, 2, 4, 8, three byte stores for B = 3 --
+// and the strip leaves with 128-bit coalesced stores.
+//
+// Transposed (B = 5, 6, 7 with four subtiles): B byte-or-halfword stores per octet, 2-way bank
+// conflicted, were what bounded those kernels (shared-memory wavefronts, not HBM).  Instead the
+// four subtiles' octets are parked as 8-byte slots in a layout from which lane m reads back the
+// four CONSECUTIVE octets 4m..4m+3 of the tile (position of octet s: row s & 3, column s >> 2;
+// rows start at `kRow`, chosen so that both the writes -- lane l of subtile u holds octet
+// 32u + octet_index(l) -- and the reads are free of bank conflicts).  Four consecutive octets are
+// 4B bytes = B whole words at word offset B*m of the tile: composed in registers, written as
+// aligned words, and the strip leaves as before.
+template <typename T, int B, int U> struct Stager {
+    static constexpr bool kTransposed = (B == 5 || B == 6 || B == 7) && U == 4;
+    static constexpr int kRow1 = sizeof(T) == 2 ? 36 : 34, kRow2 = 72, kRow3 = sizeof(T) == 2 ? 108 : 106;
+    static constexpr int kSlots = kRow3 + 32;
+    static constexpr int kPacked = U * subtile_bytes<B>();
+    // +16 bytes: strip_bits() (backward) may touch one word past the last octet.
+    static constexpr int kBytes = kTransposed ? kSlots * 8 : kPacked + 16;
+
+    // Where this lane parks its octet of subtile 0 (later subtiles: compile-time offsets).
+    static __device__ __forceinline__ uint32_t put_address(uint32_t strip, int lane) {
+        const int i = octet_index<T>(lane);
+        if constexpr (!kTransposed) return strip + B * i;
+        const int row = i & 3;
+        return strip + 8 * ((row == 0 ? 0 : row == 1 ? kRow1 : row == 2 ? kRow2 : kRow3) + (i >> 2));
+    }
+    template <int u> static __device__ __forceinline__ void put(uint32_t put_at, uint64_t octet) {
+        if constexpr (!kTransposed)
+            put_octet<B, u * subtile_bytes<B>()>(put_at, octet);
+        else
+            sts64<64 * u>(put_at, (uint32_t)octet, (uint32_t)(octet >> 32));
+    }
+
+    // After every lane has put() its U octets: move the tile's packed bytes to global memory.
+    // `strip` is the warp's strip, `out` this lane's first 16-byte chunk of the tile's state.
+    static __device__ __forceinline__ void flush(uint32_t strip, uint4 *out, int lane) {
+        __syncwarp();
+        if constexpr (kTransposed) {
+            const uint32_t mine = strip + 8 * lane;
+            const uint64_t o[4] = {lds64<0>(mine), lds64<8 * kRow1>(mine), lds64<8 * kRow2>(mine), lds64<8 * kRow3>(mine)};
+            uint32_t w[B];  // the 4B bytes of octets 4*lane .. 4*lane+3
+#pragma unroll
+            for (int k = 0; k < B; ++k) {
+                uint64_t acc = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {   // octet q covers stream bits [8Bq, 8B(q+1)) of the group
+                    const int shift = 8 * B * q - 32 * k;
+                    if (shift > -8 * B && shift < 32) acc |= shift >= 0 ? (o[q] << shift) : (o[q] >> -shift);
+                }
+                w[k] = (uint32_t)acc;
+            }
+            __syncwarp();   // every lane has read its slots: the strip can be overwritten
+            const uint32_t words = strip + 4 * B * lane;
+            if constexpr (B == 6) {
+                sts64<0>(words, w[0], w[1]), sts64<8>(words, w[2], w[3]), sts64<16>(words, w[4], w[5]);
+            } else {
+                sts32<0>(words, w[0]), sts32<4>(words, w[1]), sts32<8>(words, w[2]), sts32<12>(words, w[3]);
+                sts32<16>(words, w[4]);
+                if constexpr (B == 7) sts32<20>(words, w[5]), sts32<24>(words, w[6]);
+            }
+            __syncwarp();
+        }
+        constexpr int kChunks = kPacked / 16;
+        const uint32_t src = strip + 16 * lane;
+        if constexpr (kChunks >= 32) stg_stream(out, lds128<0>(src));
+        if constexpr (kChunks >= 64) stg_stream(out + 32, lds128<512>(src));
+        if constexpr (kChunks >= 96) stg_stream(out + 64, lds128<1024>(src));
+        if constexpr (kChunks >= 128) stg_stream(out + 96, lds128<1536>(src));
+        constexpr int kFull = kChunks / 32 * 32;
+        if constexpr (kChunks > kFull)
+            if (lane < kChunks - kFull) stg_stream(out + kFull, lds128<16 * kFull>(src));
+        __syncwarp();
+    }
+};
 
 // Backward: fetch `nbits` (<= 32) stream bits starting at bit `pos` of the strip.
 // The strip is read as aligned 32-bit words; one word of slack past the end is required.
@@ -226,30 +357,29 @@ template <int B, int U> struct StripStorage {
     alignas(16) uint8_t bytes[kWarps][kBytes];
 };
 
-// One warp, `N` consecutive subtiles starting at subtile index `sub`.
-template <class Op, typename T, int N>
-__device__ __forceinline__ void forward_chunk(const Op &op, const T *x, T *y, uint8_t *state,
-                                              uint8_t *strip, int64_t sub, int lane) {
-    constexpr int B = Op::kBits;
-    constexpr int kBytes = N * subtile_bytes<B>();
-    const T *xt = x + sub * kSubtile;
-    T *yt = y + sub * kSubtile;
+// One warp, `N` consecutive subtiles.  `xl` / `yl` / `out`: this lane's first 128-bit vector of
+// the tile's input, output and packed state; `strip` / `put_at`: the warp's strip and this lane's
+// parking address in it (shared-space addresses).
+template <class Op, typename T, int N, bool kExact, int u = 0>
+__device__ __forceinline__ void forward_subtiles(const Op &op, const typename Op::Scratch &scratch,
+                                                 float (&v)[N][8], uint4 *yl, uint32_t put_at, int lane) {
+    if constexpr (u < N) {
+        uint32_t half[2];
+        op.template apply<kExact>(scratch, v[u], half);
+        Subtile<T>::store_at(yl + u * Subtile<T>::kVectors, v[u]);
+        Stager<T, Op::kBits, N>::template put<u>(put_at, lane_octet<T, Op::kBits>(lane, half[0], half[1]));
+        forward_subtiles<Op, T, N, kExact, u + 1>(op, scratch, v, yl, put_at, lane);
+    }
+}
+
+template <class Op, typename T, int N, bool kExact>
+__device__ __forceinline__ void forward_chunk(const Op &op, const typename Op::Scratch &scratch, const uint4 *xl,
+                                              uint4 *yl, uint4 *out, uint32_t strip, uint32_t put_at, int lane) {
     float v[N][8];
 #pragma unroll
-    for (int u = 0; u < N; ++u) Subtile<T>::load(xt + u * kSubtile, lane, v[u]);
-#pragma unroll
-    for (int u = 0; u < N; ++u) {
-        uint32_t code[8];
-        op.apply(v[u], code);
-        Subtile<T>::store(yt + u * kSubtile, lane, v[u]);
-        stage_codes<T, B>(strip + u * subtile_bytes<B>(), lane, code);
-    }
-    __syncwarp();
-    uint4 *out = reinterpret_cast<uint4 *>(state + sub * (int64_t)subtile_bytes<B>());
-    const uint4 *src = reinterpret_cast<const uint4 *>(strip);
-#pragma unroll
-    for (int i = lane; i < kBytes / 16; i += 32) stg_stream(out + i, src[i]);
-    __syncwarp();
+    for (int u = 0; u < N; ++u) Subtile<T>::load_at(xl + u * Subtile<T>::kVectors, v[u]);
+    forward_subtiles<Op, T, N, kExact>(op, scratch, v, yl, put_at, lane);
+    Stager<T, Op::kBits, N>::flush(strip, out, lane);
 }
 
 template <class Op, typename T, int N>
@@ -283,23 +413,62 @@ __device__ __forceinline__ void backward_chunk(const Op &op, const uint8_t *stat
 // (strided, so that the grid sweeps memory as one window); what is left over (< one tile per
 // warp) is handed out in single subtiles, which bounds the imbalance at 256 elements per warp
 // instead of U * 256.
+// Keeps a loop-invariant address in its register: without it the compiler rebuilds warp / lane /
+// strip addresses from the thread index inside the loop (the kernels are register-capped).
+__device__ __forceinline__ uint32_t pinned(uint32_t v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
+template <typename P> __device__ __forceinline__ P *pinned(P *p) {
+    asm volatile("" : "+l"(p));
+    return p;
+}
+
+// The persistent loop of one warp.  kExact: the op's slow path (tables whose borders the cell
+// look-up cannot separate) -- chosen once per block, outside the loop, so that the hot loop
+// carries no branch.
+template <class Op, typename T, int U, bool kExact>
+__device__ __forceinline__ void forward_loop(const Op &op, const typename Op::Scratch &scratch, const T *x, T *y,
+                                             uint8_t *state, int64_t ntiles, uint32_t strip) {
+    constexpr int B = Op::kBits;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+    const int64_t me = (int64_t)blockIdx.x * kWarps + warp;
+    const int64_t rounds = ntiles / nwarps;
+    constexpr int kVectors = U * Subtile<T>::kVectors, kChunks = U * subtile_bytes<B>() / 16;
+    // full tiles: pointers advance by a constant stride, the loop carries no index arithmetic
+    if (rounds > 0) {
+        const uint4 *xl = pinned(reinterpret_cast<const uint4 *>(x) + me * kVectors + lane);
+        uint4 *yl = pinned(reinterpret_cast<uint4 *>(y) + me * kVectors + lane);
+        uint4 *out = pinned(reinterpret_cast<uint4 *>(state) + me * kChunks + lane);
+        const uint32_t put_at = pinned(Stager<T, B, U>::put_address(strip, lane));
+        const int64_t step = nwarps * kVectors, out_step = nwarps * kChunks;
+        for (int64_t r = 0; r < rounds; ++r, xl += step, yl += step, out += out_step)
+            forward_chunk<Op, T, U, kExact>(op, scratch, xl, yl, out, strip, put_at, lane);
+    }
+    // what is left over (< one tile per warp) is handed out in single subtiles
+    const uint32_t put_at = Stager<T, B, 1>::put_address(strip, lane);
+    for (int64_t sub = rounds * nwarps * U + me; sub < ntiles * U; sub += nwarps)
+        forward_chunk<Op, T, 1, kExact>(
+            op, scratch, reinterpret_cast<const uint4 *>(x) + sub * Subtile<T>::kVectors + lane,
+            reinterpret_cast<uint4 *>(y) + sub * Subtile<T>::kVectors + lane,
+            reinterpret_cast<uint4 *>(state) + sub * (subtile_bytes<B>() / 16) + lane, strip, put_at, lane);
+}
+
 template <class Op, typename T, int U, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) forward_tiles_kernel(const T *x, T *y, uint8_t *state,
                                                                 int64_t ntiles, Op op) {
     constexpr int B = Op::kBits;
-    __shared__ StripStorage<B, U> strips;
+    constexpr int kStrip = Stager<T, B, U>::kBytes > Stager<T, B, 1>::kBytes ? Stager<T, B, U>::kBytes
+                                                                              : Stager<T, B, 1>::kBytes;
+    __shared__ alignas(16) uint8_t strips[kWarps][(kStrip + 15) / 16 * 16];
     __shared__ typename Op::Scratch scratch;
     op.prepare(scratch);
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t *strip = strips.bytes[warp];
-    const int64_t nwarps = (int64_t)gridDim.x * kWarps;
-    const int64_t me = (int64_t)blockIdx.x * kWarps + warp;
-    const int64_t even = ntiles / nwarps * nwarps;
-    for (int64_t tile = me; tile < even; tile += nwarps)
-        forward_chunk<Op, T, U>(op, x, y, state, strip, tile * U, lane);
-    for (int64_t sub = even * U + me; sub < ntiles * U; sub += nwarps)
-        forward_chunk<Op, T, 1>(op, x, y, state, strip, sub, lane);
+    const uint32_t strip = (uint32_t)__cvta_generic_to_shared(strips[threadIdx.x >> 5]);
+    if (op.exact())
+        forward_loop<Op, T, U, true>(op, scratch, x, y, state, ntiles, strip);
+    else
+        forward_loop<Op, T, U, false>(op, scratch, x, y, state, ntiles, strip);
 }
 
 template <class Op, typename T, int U, int MINB>
@@ -335,19 +504,17 @@ __global__ void __launch_bounds__(kThreads) forward_ragged_kernel(const T *x, T 
     for (int64_t o = (int64_t)blockIdx.x * kThreads + threadIdx.x; o < noctets;
          o += (int64_t)gridDim.x * kThreads) {
         const int64_t e0 = first + 8 * o;
-        uint64_t octet = 0;
         float v[8];
-        uint32_t code[8];
+        uint32_t half[2];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = e0 + j < n ? to_float<T>(x[e0 + j]) : 0.0f;
-        op.apply(v, code);
+        if (op.exact()) op.template apply<true>(scratch, v, half); else op.template apply<false>(scratch, v, half);
+        uint64_t octet = (uint64_t)half[0] | ((uint64_t)half[1] << (4 * B));
+        const int valid = n - e0 < 8 ? (int)(n - e0) : 8;   // pad bits of the last octet stay zero
+        if (valid < 8) octet &= ((uint64_t)1 << (B * valid)) - 1;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (e0 + j < n) {
-                y[e0 + j] = from_float<T>(v[j]);
-                octet |= (uint64_t)code[j] << (B * j);
-            }
-        }
+        for (int j = 0; j < 8; ++j)
+            if (e0 + j < n) y[e0 + j] = from_float<T>(v[j]);
         const int64_t b0 = (e0 / 8) * B;
 #pragma unroll
         for (int k = 0; k < B; ++k)
