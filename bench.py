@@ -13,6 +13,11 @@ backward (gin = factor(mask) * gout) -- six kernel launches through the C ABI
 on the data path).  Inputs are 8x larger than L2, so no flush is needed between iterations.
 
 One JSON line on stdout (rank 0); see the contract in the task description for the keys.
+Beyond the contract the line carries `rooflines` -- one entry per kernel of the path (the six
+mask kernels from events inside the timed region; 3-bit GELU forward / backward in fp32 and bf16
+on 128 x 128 x 3072 and the tcgen05 projection kernel from side runs, N = 1 only) -- and
+`extra.roberta`: RoBERTa-base 128 x 128 step time and peak memory for {vanilla, 3-bit GELU,
+RandomizedLinear 0.2, both} in fp32 and bf16 (child processes, benchmarks/roberta_step.py).
 """
 from __future__ import annotations
 
@@ -44,6 +49,9 @@ CONFIG = {
     'algorithmic_bytes_per_step_per_gpu': BYTES_PER_STEP,
     'l2_policy': 'inputs (2 GiB read per pass pair) are larger than the 126 MB L2; no flush needed',
     'parallelism': 'batch-sharded replicas, no collective on the data path',
+    'reference_arm': 'the CPU path runs on rank 0 only, with every host core the process may use, on a '
+                     'sample sized for ~90 s (a rate: GB/s of the same three functions, fwd+bwd); it does '
+                     'not depend on --gpus',
 }
 
 
@@ -154,6 +162,10 @@ def run_reference_arm(args, rank, world):
     """`--impl reference`: the reference CPU path on the host cores, rank 0 only."""
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is one process that may use the
+    # host exactly as it does at --gpus 1 (torch's default thread count), whatever --gpus says
+    if world > 1:
+        os.environ.pop('OMP_NUM_THREADS', None)
     import torch
 
     import oracle
@@ -187,7 +199,7 @@ def run_reference_arm(args, rank, world):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': elapsed / args.steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
-        'data': 'synthetic', 'config': CONFIG,
+        'data': 'synthetic', 'config': dict(CONFIG, reference_sample_elements=sample, reference_threads=cores, n_gpus_independent=True),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind,
                          'sample': sample_txt},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -217,6 +229,78 @@ def cpu_baseline_leg():
             'sample': f'{reps} steps over {sample} bf16 elements ({sample * 2 >> 20} MiB of the 1 GiB '
                       f'workload), {elapsed:.1f} s; torch CPU ops + fewbit::Deflate/Inflate '
                       f'(fewbit/cpu/codec.h, single-threaded by construction)'}
+
+
+def load_traffic():
+    """DRAM bytes per launch from the committed ncu capture (tools/ncu_table.py --traffic)."""
+    path = ROOT / 'profiles' / 'ncu_traffic.json'
+    try:
+        return json.loads(path.read_text()) if path.exists() else {}
+    except Exception:  # noqa: BLE001
+        return {}
+
+
+def traffic_name(kernel):
+    # every 1-bit backward is the same kernel (MaskFactorOp) with other constants
+    return 'relu_backward' if kernel.endswith('_backward') and kernel.split('_')[0] in ('relu', 'leaky', 'hardtanh') \
+        else kernel
+
+
+def roofline_entry(kernel, nbytes, ms, peak, traffic, where, bound='hbm', unit='GB/s', scale=1e9, **more):
+    achieved = nbytes / (ms / 1e3) / scale
+    entry = {'kernel': kernel, 'bound': bound, 'achieved': achieved, 'peak': peak, 'unit': unit,
+             'frac': achieved / peak, 'traffic': traffic, 'avg_launch_ms': ms, 'measured': where}
+    entry['algorithmic_bytes_per_launch' if bound == 'hbm' else 'flops_per_launch'] = nbytes
+    entry.update(more)
+    return entry
+
+
+def cross_device_check(local_rank, world):
+    """At N >= 2: run the operator on a tensor that lives on ANOTHER device than the current one
+    and compare with torch's own bucket search -- the kernels must follow the tensor (device
+    guard + that device's stream), which a 1-GPU box cannot show."""
+    import torch
+
+    import fewbit_b200 as fewbit
+    try:
+        other = torch.device('cuda', (local_rank + 1) % world)
+        borders, levels = fewbit.functional.store.get('gelu', 3, other, torch.float32)
+        bounds = borders[1:-1].contiguous()
+        gen = torch.Generator(other).manual_seed(99 + local_rank)
+        x = torch.randn(1 << 20, device=other, generator=gen) * 2
+        leaf = x.clone().requires_grad_()
+        y = torch.ops.fewbit.gelu(leaf * 1.0, bounds, levels)
+        y.sum().backward()
+        torch.cuda.synchronize(other)
+        codes = torch.searchsorted(bounds, x, right=False)
+        ok = (torch.equal(leaf.grad, levels[codes]) and y.device == other
+              and torch.allclose(y, torch.nn.functional.gelu(x), atol=1e-6, rtol=1e-5)
+              and torch.cuda.current_device() == local_rank)
+        return 'ok' if ok else 'mismatch'
+    except Exception as exc:  # noqa: BLE001
+        return f'{type(exc).__name__}: {exc}'
+
+
+def roberta_block():
+    """RoBERTa-base (random init, synthetic 128 x 128 batch) step time and peak memory, the other half
+    of BASELINE.json's metric: one child process per variant (benchmarks/roberta_step.py, the
+    reference's measurement method benchmark/benchmark.py:165-188), fp32 and bf16."""
+    out = {}
+    for dtype in ('fp32', 'bf16'):
+        dest = ROOT / 'gpurun_out' / f'bench_roberta_{dtype}.json'
+        try:
+            dest.parent.mkdir(exist_ok=True)
+            subprocess.run([sys.executable, str(ROOT / 'benchmarks' / 'roberta_step.py'), '--dtype', dtype,
+                            '--steps', '3', '--json', str(dest)], capture_output=True, text=True, timeout=240)
+            rows = json.loads(dest.read_text())['results']
+            out[dtype] = [{k: r.get(k) for k in ('variant', 'step_ms', 'peak_gib', 'peak_vs_vanilla_pct',
+                                                  'reference_published_pct', 'error') if r.get(k) is not None}
+                          for r in rows]
+        except Exception as exc:  # noqa: BLE001
+            out[dtype] = {'error': f'{type(exc).__name__}: {exc}'}
+    out['note'] = ('batch 128 x 128 tokens, AdamW, median of 3 steps after 2 warm-ups; peak = max_memory_allocated '
+                   'minus the allocation before the model is built; reference_published_pct = README.md:18-27')
+    return out
 
 
 # ------------------------------------------------------------------------ our arm ----
@@ -315,32 +399,38 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     elapsed_ms, e2e_ms = times.tolist()
 
-    extra = {}
+    cross = cross_device_check(local_rank, world) if world > 1 else None
+    if world > 1:
+        flag = torch.tensor([1.0 if cross == 'ok' else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        cross = 'ok on every rank' if flag.item() == 1.0 else f'FAILED (rank {rank}: {cross})'
+
+    extra, side_rooflines = {}, []
     if rank == 0 and world == 1:
-        extra = side_measurements(dev)
+        peak, _ = measured_peak()
+        traffic_table = load_traffic()
+        extra, side_rooflines = side_measurements(dev, peak, traffic_table)
 
     if rank == 0:
         peak, peak_src = measured_peak()
+        traffic_table = load_traffic()
         value = world * BYTES_PER_STEP * args.steps / (elapsed_ms / 1e3) / 1e9
         e2e_value = world * BYTES_PER_STEP * e2e_steps / (e2e_ms / 1e3) / 1e9
         dominant = 'relu_forward'
-        achieved = BYTES_PER_PASS / (kernel_ms[dominant] / 1e3) / 1e9
-        traffic = None
-        tpath = ROOT / 'profiles' / 'ncu_traffic.json'
-        if tpath.exists():
-            try:
-                traffic = json.loads(tpath.read_text()).get(dominant)
-            except Exception:  # noqa: BLE001
-                traffic = None
+        rooflines = [roofline_entry(k, BYTES_PER_PASS, v, peak, traffic_table.get(traffic_name(k)),
+                                    where='CUDA events inside the timed region, 1 GiB bf16 tensor')
+                     for k, v in kernel_ms.items()] + side_rooflines
+        head = next(r for r in rooflines if r['kernel'] == dominant)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': elapsed_ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
             'data': 'synthetic', 'config': CONFIG,
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': traffic, 'kernel': dominant,
+            'roofline': {'bound': 'hbm', 'achieved': head['achieved'], 'peak': peak, 'unit': 'GB/s',
+                         'frac': head['frac'], 'traffic': head['traffic'], 'kernel': dominant,
                          'peak_source': peak_src, 'algorithmic_bytes_per_launch': BYTES_PER_PASS,
                          'avg_launch_ms': kernel_ms[dominant]},
+            'rooflines': rooflines,
             'kernels_GBps': {k: BYTES_PER_PASS / (v / 1e3) / 1e9 for k, v in kernel_ms.items()},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'steps': e2e_steps,
                     'h2d_bytes_per_step': 2 * len(FUNCS) * N_ELEMS * 2,
@@ -350,6 +440,8 @@ def run_ours(args, rank, local_rank, world):
             'gpu_launches': launches,
             'clocks': clocks,
         }
+        if cross is not None:
+            line['cross_device_check'] = cross
         if world == 1:
             line['cpu_baseline'] = cpu_baseline_leg()
         if extra:
@@ -360,15 +452,38 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def side_measurements(dev):
-    """Not part of the headline: 3-bit GELU on 128 x 128 x 3072 (configs[0]/[2]), fp32 and bf16,
-    forward and backward GB/s, median of 20 after 5 warm-ups."""
+def side_measurements(dev, peak, traffic_table):
+    """Not part of the headline: the other kernels of the path, each timed alone (N = 1 only).
+
+    3-bit GELU on 128 x 128 x 3072 (configs[0] / [2]), fp32 and bf16, forward and backward: median of
+    20 launches; before every launch the L2 is flushed by READING a 256 MiB buffer, so the inputs
+    come from HBM and the L2 holds clean lines (flushing by writing would leave 126 MB of dirty
+    lines for the timed kernel to evict; back-to-back launches would leave its own ~50 MB of
+    write-back in L2 -- the two differ by 5-10 % on a 100-200 MB tensor).
+    The projection S X on tcgen05 (configs[4] shape: N = 16384 tokens, P = 3276 rows, D = 768): CUDA
+    events around the C-ABI call with output and workspace preallocated, i.e. the projection kernel
+    plus its split-K reduction and nothing else."""
     import torch
 
     from fewbit_b200 import native
     from fewbit_b200.functional import store
-    out = {}
+    out, rooflines = {}, []
     n = 128 * 128 * 3072
+    flush = torch.ones(256 << 18, dtype=torch.float32, device=dev)     # 256 MiB
+    sink = torch.zeros((), dtype=torch.float32, device=dev)
+
+    def timed(fn, reps=25, skip=5):
+        ts = []
+        for it in range(reps):
+            sink.copy_(flush.sum())                                    # read 256 MiB > L2
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            if it >= skip:
+                ts.append(a.elapsed_time(b))
+        return statistics.median(ts)
+
+    where = '128x128x3072 elements, median of 20 single launches, L2 flushed by reading 256 MiB before each'
     for tag, dtype, es in (('f32', torch.float32, 4), ('bf16', torch.bfloat16, 2)):
         borders, levels = store.get('gelu', 3, dev, dtype)
         bounds = borders[1:-1].contiguous()
@@ -377,39 +492,43 @@ def side_measurements(dev):
         y, gin = torch.empty_like(x), torch.empty_like(g)
         state = native.new_state(x, 3)
         nbytes = n * (2 * es) + n * 3 // 8
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-        for label, fn in (('fwd', lambda: native.stepwise_forward('gelu', x, y, state, 3, bounds)),
-                          ('bwd', lambda: native.stepwise_backward(state, g, gin, 3, levels))):
-            ts = []
-            for it in range(25):
-                flush.zero_()                                  # 256 MiB > L2: cold inputs
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(); fn(); b.record()
-                torch.cuda.synchronize()
-                if it >= 5:
-                    ts.append(a.elapsed_time(b))
-            out[f'gelu3_{tag}_{label}_GBps'] = nbytes / (statistics.median(ts) / 1e3) / 1e9
-        del x, g, y, gin, state, flush
-    out['note'] = '128x128x3072 elements, median of 20 launches, L2 flushed between launches'
-    # RandomizedLinear's projection (configs[4] shape: N = 16384 tokens, P = 3276 rows, D = 768),
-    # the one tensor-pipe kernel of the path: TFLOP/s = 2 P N D / time, against the measured bf16 peak.
+        for label, key, fn in (('fwd', f'gelu3_{tag}_forward', lambda: native.stepwise_forward('gelu', x, y, state, 3, bounds)),
+                               ('bwd', f'levels3_{tag}_backward', lambda: native.stepwise_backward(state, g, gin, 3, levels))):
+            ms = timed(fn)
+            out[f'gelu3_{tag}_{label}_GBps'] = nbytes / (ms / 1e3) / 1e9
+            rooflines.append(roofline_entry(f'gelu3_{tag}_{"forward" if label == "fwd" else "backward"}', nbytes, ms,
+                                            peak, traffic_table.get(key), where))
+        del x, g, y, gin, state
+    out['note'] = where
     tokens, rows, features = 16384, 3276, 768
     x = torch.randn(tokens, features, device=dev).to(torch.bfloat16)
-    for kind in ('gaussian', 'rademacher'):
-        ts = []
-        for it in range(25):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); native.sketch_forward(x, rows, 1, it, kind, 1.0 / rows); b.record()
-            torch.cuda.synchronize()
-            if it >= 5:
-                ts.append(a.elapsed_time(b))
-        out[f'sketch_{kind}_D768_TFLOPs'] = 2.0 * rows * tokens * features / (statistics.median(ts) / 1e3) / 1e12
+    result = torch.empty(rows, features, dtype=torch.float32, device=dev)
+    workspace = native.sketch_workspace(x, rows)
+    tensor_peak = None
     peaks = ROOT / 'MEASURED_PEAKS.json'
     if peaks.exists():
-        out['sketch_peak_bf16_TFLOPs'] = json.loads(peaks.read_text()).get('bf16_tflops')
-    out['sketch_note'] = ('one call at a time, synchronised, including the workspace allocation and the split-K '
-                          'reduce kernel; back to back: benchmarks/sketch_bench.py, profiles/r01_sketch_bench.json')
-    return out
+        tensor_peak = json.loads(peaks.read_text()).get('bf16_tflops')
+    tensor_peak = tensor_peak or 1590.0
+    for kind in ('gaussian', 'rademacher'):
+        calls = [0]
+
+        def run():
+            calls[0] += 1
+            native.sketch_forward(x, rows, 1, 4 * calls[0], kind, 1.0 / rows, out=result, workspace=workspace)
+
+        ms = timed(run)
+        flops = 2.0 * rows * tokens * features
+        out[f'sketch_{kind}_D768_TFLOPs'] = flops / (ms / 1e3) / 1e12
+        rooflines.append(roofline_entry(
+            f'sketch_{kind}_D768', flops, ms, tensor_peak, traffic_table.get('sketch_kernel'),
+            'N=16384 P=3276 D=768 bf16, median of 20 calls of fewbit_sketch_forward with preallocated output and '
+            'workspace (projection kernel + split-K reduction), L2 flushed by reading before each',
+            bound='tensor', unit='TFLOP/s', scale=1e12, peak_source='MEASURED_PEAKS.json bf16_tflops (burst)'))
+    out['sketch_peak_bf16_TFLOPs'] = tensor_peak
+    del flush
+    torch.cuda.empty_cache()
+    out['roberta'] = roberta_block()
+    return out, rooflines
 
 
 def main():

@@ -52,7 +52,8 @@ if which == 'r2fwd':
     n = 128 * 128 * 3072
     x = (torch.randn(n, device=dev) * 2).to(torch.bfloat16)
     y = torch.empty_like(x)
-    for name, bits in (('gelu', 3), ('gelu', 7), ('hardswish', 7), ('gelu', 5), ('gelu', 8), ('tanh', 3)):
+    cells = [c.split(':') for c in (sys.argv[3] if len(sys.argv) > 3 else 'gelu:3,gelu:7,hardswish:7,gelu:5,gelu:8,tanh:3').split(',')]
+    for name, bits in ((c[0], int(c[1])) for c in cells):
         borders, _ = _store.get(name, bits, dev, torch.bfloat16)
         state = native.new_state(x, bits)
         for _ in range(reps):

@@ -31,19 +31,27 @@ constexpr int kSubtile = 256;  // elements per warp per round of 128-bit loads
 #ifndef FEWBIT_LD_MODE
 #define FEWBIT_LD_MODE 1  // 0: ld.global   1: ld.global.L1::no_allocate   2: ld.global.cs
 #endif
+#ifndef FEWBIT_PREFETCH
+// Input prefetch of the math-heavy bf16 forward kernels.  0: load a tile, compute it.
+// 1: software pipeline through registers.  2: cp.async ring in shared memory (the default).
+#define FEWBIT_PREFETCH 2
+#endif
 #ifndef FEWBIT_ST_MODE
 #define FEWBIT_ST_MODE 1  // 0: st.global   1: st.global.L1::no_allocate   2: st.global.cs
 #endif
 
+// Not `volatile`: a load is a pure function of its address as far as these kernels go (every
+// element is read once, before its own in-place overwrite, which depends on the loaded value), and
+// the scheduler must be free to hoist the prefetching loads above earlier stores.
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
     uint4 r;
     // Plain (coherent) load: x and y may alias, so the read-only .nc path is off limits.
 #if FEWBIT_LD_MODE == 0
-    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];"
 #elif FEWBIT_LD_MODE == 1
-    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
 #else
-    asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];"
 #endif
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
@@ -98,14 +106,19 @@ template <> struct Subtile<float> {
         v[4] = __uint_as_float(b.x), v[5] = __uint_as_float(b.y);
         v[6] = __uint_as_float(b.z), v[7] = __uint_as_float(b.w);
     }
-    // the same through this lane's pointer (first vector of the subtile + lane)
-    static __device__ __forceinline__ void load_at(const uint4 *p, float (&v)[8]) {
-        uint4 a = ldg_stream(p), b = ldg_stream(p + 32);
-        v[0] = __uint_as_float(a.x), v[1] = __uint_as_float(a.y);
-        v[2] = __uint_as_float(a.z), v[3] = __uint_as_float(a.w);
-        v[4] = __uint_as_float(b.x), v[5] = __uint_as_float(b.y);
-        v[6] = __uint_as_float(b.z), v[7] = __uint_as_float(b.w);
+    // the same through this lane's pointer (first vector of the subtile + lane), and split into
+    // the load proper and the conversion (the pipelined loop keeps raw vectors in flight)
+    struct Raw {
+        uint4 a, b;
+    };
+    static __device__ __forceinline__ Raw fetch(const uint4 *p) { return Raw{ldg_stream(p), ldg_stream(p + 32)}; }
+    static __device__ __forceinline__ void widen(const Raw &r, float (&v)[8]) {
+        v[0] = __uint_as_float(r.a.x), v[1] = __uint_as_float(r.a.y);
+        v[2] = __uint_as_float(r.a.z), v[3] = __uint_as_float(r.a.w);
+        v[4] = __uint_as_float(r.b.x), v[5] = __uint_as_float(r.b.y);
+        v[6] = __uint_as_float(r.b.z), v[7] = __uint_as_float(r.b.w);
     }
+    static __device__ __forceinline__ void load_at(const uint4 *p, float (&v)[8]) { widen(fetch(p), v); }
     static __device__ __forceinline__ void store_at(uint4 *p, const float (&v)[8]) {
         stg_stream(p, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]),
                                  __float_as_uint(v[2]), __float_as_uint(v[3])));
@@ -129,11 +142,15 @@ template <> struct Subtile<__nv_bfloat16> {
         v[0] = bf16_lo(a.x), v[1] = bf16_hi(a.x), v[2] = bf16_lo(a.y), v[3] = bf16_hi(a.y);
         v[4] = bf16_lo(a.z), v[5] = bf16_hi(a.z), v[6] = bf16_lo(a.w), v[7] = bf16_hi(a.w);
     }
-    static __device__ __forceinline__ void load_at(const uint4 *p, float (&v)[8]) {
-        uint4 a = ldg_stream(p);
-        v[0] = bf16_lo(a.x), v[1] = bf16_hi(a.x), v[2] = bf16_lo(a.y), v[3] = bf16_hi(a.y);
-        v[4] = bf16_lo(a.z), v[5] = bf16_hi(a.z), v[6] = bf16_lo(a.w), v[7] = bf16_hi(a.w);
+    struct Raw {
+        uint4 a;
+    };
+    static __device__ __forceinline__ Raw fetch(const uint4 *p) { return Raw{ldg_stream(p)}; }
+    static __device__ __forceinline__ void widen(const Raw &r, float (&v)[8]) {
+        v[0] = bf16_lo(r.a.x), v[1] = bf16_hi(r.a.x), v[2] = bf16_lo(r.a.y), v[3] = bf16_hi(r.a.y);
+        v[4] = bf16_lo(r.a.z), v[5] = bf16_hi(r.a.z), v[6] = bf16_lo(r.a.w), v[7] = bf16_hi(r.a.w);
     }
+    static __device__ __forceinline__ void load_at(const uint4 *p, float (&v)[8]) { widen(fetch(p), v); }
     static __device__ __forceinline__ void store_at(uint4 *p, const float (&v)[8]) {
         stg_stream(p, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
                                  pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
@@ -206,6 +223,16 @@ template <int kOffset> __device__ __forceinline__ uint4 lds128(uint32_t a) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a), "n"(kOffset) : "memory");
     return r;
+}
+
+// Asynchronous 16-byte copy global -> shared (LDGSTS, L1 bypassed): no register holds the data in
+// flight, so nothing tempts the scheduler to delay the load until just before its use.
+template <int kOffset> __device__ __forceinline__ void copy_async16(uint32_t dst, const uint4 *src) {
+    asm volatile("cp.async.cg.shared.global [%0+%2], [%1], 16;" ::"r"(dst), "l"(src), "n"(kOffset) : "memory");
+}
+__device__ __forceinline__ void copy_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending> __device__ __forceinline__ void copy_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
 }
 
 // Write the low B bytes of `octet` to the (B-byte aligned) shared-memory address a + kOffset.
@@ -424,6 +451,23 @@ template <typename P> __device__ __forceinline__ P *pinned(P *p) {
     return p;
 }
 
+// Subtiles u0 .. u0+H-1 of a tile whose raw vectors are already in registers; their octets are
+// parked at positions p0 .. p0+H-1 of stager S.
+template <class Op, typename T, class S, bool kExact, int u0, int p0, int H, int h = 0>
+__device__ __forceinline__ void forward_half(const Op &op, const typename Op::Scratch &scratch,
+                                             const typename Subtile<T>::Raw (&raw)[H], uint4 *yl, uint32_t put_at,
+                                             int lane) {
+    if constexpr (h < H) {
+        float v[8];
+        uint32_t half[2];
+        Subtile<T>::widen(raw[h], v);
+        op.template apply<kExact>(scratch, v, half);
+        Subtile<T>::store_at(yl + (u0 + h) * Subtile<T>::kVectors, v);
+        S::template put<p0 + h>(put_at, lane_octet<T, Op::kBits>(lane, half[0], half[1]));
+        forward_half<Op, T, S, kExact, u0, p0, H, h + 1>(op, scratch, raw, yl, put_at, lane);
+    }
+}
+
 // The persistent loop of one warp.  kExact: the op's slow path (tables whose borders the cell
 // look-up cannot separate) -- chosen once per block, outside the loop, so that the hot loop
 // carries no branch.
@@ -443,8 +487,25 @@ __device__ __forceinline__ void forward_loop(const Op &op, const typename Op::Sc
         uint4 *out = pinned(reinterpret_cast<uint4 *>(state) + me * kChunks + lane);
         const uint32_t put_at = pinned(Stager<T, B, U>::put_address(strip, lane));
         const int64_t step = nwarps * kVectors, out_step = nwarps * kChunks;
-        for (int64_t r = 0; r < rounds; ++r, xl += step, yl += step, out += out_step)
-            forward_chunk<Op, T, U, kExact>(op, scratch, xl, yl, out, strip, put_at, lane);
+        if constexpr (Op::kHeavy && U % 2 == 0 && FEWBIT_PREFETCH == 1) {
+            constexpr int H = U / 2, kHalf = H * Subtile<T>::kVectors;
+            typename Subtile<T>::Raw first[H], second[H];
+#pragma unroll
+            for (int h = 0; h < H; ++h) first[h] = Subtile<T>::fetch(xl + h * Subtile<T>::kVectors);
+            for (int64_t r = 0; r < rounds; ++r, yl += step, out += out_step) {
+#pragma unroll
+                for (int h = 0; h < H; ++h) second[h] = Subtile<T>::fetch(xl + kHalf + h * Subtile<T>::kVectors);
+                forward_half<Op, T, Stager<T, B, U>, kExact, 0, 0, H>(op, scratch, first, yl, put_at, lane);
+                if (r + 1 < rounds) xl += step;     // the last round fetches its own first half again
+#pragma unroll
+                for (int h = 0; h < H; ++h) first[h] = Subtile<T>::fetch(xl + h * Subtile<T>::kVectors);
+                forward_half<Op, T, Stager<T, B, U>, kExact, H, H, H>(op, scratch, second, yl, put_at, lane);
+                Stager<T, B, U>::flush(strip, out, lane);
+            }
+        } else {
+            for (int64_t r = 0; r < rounds; ++r, xl += step, yl += step, out += out_step)
+                forward_chunk<Op, T, U, kExact>(op, scratch, xl, yl, out, strip, put_at, lane);
+        }
     }
     // what is left over (< one tile per warp) is handed out in single subtiles
     const uint32_t put_at = Stager<T, B, 1>::put_address(strip, lane);
@@ -455,20 +516,111 @@ __device__ __forceinline__ void forward_loop(const Op &op, const typename Op::Sc
             reinterpret_cast<uint4 *>(state) + sub * (subtile_bytes<B>() / 16) + lane, strip, put_at, lane);
 }
 
+// Which forward kernels stream their input through the cp.async ring (forward_stream below).
+template <class Op, typename T, int U> constexpr bool streams_input() {
+    return Op::kHeavy && sizeof(T) == 2 && U == 4 && FEWBIT_PREFETCH == 2;
+}
+
+// The math-heavy bf16 forward kernels: the same work, streamed.
+//
+// Input travels global -> shared by cp.async in HALF tiles (two subtiles, 1 KB), two halves ahead of
+// the one being computed, through a ring of three per-warp slots; every lane copies and later reads
+// back its own 16 bytes of each subtile, so no cross-lane synchronisation is involved, and a slot
+// is overwritten one half after it was read, when the instructions that consumed those registers
+// have long issued.  (Loading a whole tile into registers and then computing it left each warp
+// with nothing in flight during its compute phase: ncu showed 4.3 of the 6.5 resident warps per
+// scheduler waiting on global loads at any time, 58 % issue utilisation; loads prefetched into
+// registers were sunk by the compiler to just before their use.)
+//
+// Work is dealt out in units of one half tile -- one tile for the 5/6/7-bit kernels, whose packed
+// bytes are assembled from four subtiles -- strided over the warps of the grid (unit u belongs to
+// warp u mod nwarps, so the grid still sweeps memory as one window); warps differ by at most one
+// unit, i.e. 512 elements: with ~20 halves per warp on a 100 MB tensor, dealing whole tiles and
+// mopping up with unpipelined single subtiles cost ~10 % in the tail.
+template <class Op, typename T, bool kExact>
+__device__ __forceinline__ void forward_stream(const Op &op, const typename Op::Scratch &scratch, const T *x, T *y,
+                                               uint8_t *state, int64_t nhalves, uint32_t strip, uint32_t ring) {
+    constexpr int B = Op::kBits, H = 2;
+    constexpr bool kWhole = Stager<T, B, 2 * H>::kTransposed;      // unit = tile (two halves)
+    constexpr int kParts = kWhole ? 2 : 1;
+    using S = Stager<T, B, kParts * H>;
+    constexpr int kHalf = H * Subtile<T>::kVectors;                // 128-bit vectors per half
+    constexpr int kHalfChunks = H * subtile_bytes<B>() / 16;       // 16-byte chunks of packed state per half
+    constexpr int kSlot = H * 512;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+    const int64_t me = (int64_t)blockIdx.x * kWarps + warp;
+    const int64_t nunits = nhalves / kParts;
+    if (me >= nunits) return;
+    const int64_t mine = (nunits - me + nwarps - 1) / nwarps;      // units of this warp
+    const int64_t unit_step = nwarps * kParts * kHalf;             // vectors from one unit to the next
+
+    uint4 *yl = pinned(reinterpret_cast<uint4 *>(y) + me * (kParts * kHalf) + lane);
+    uint4 *out = pinned(reinterpret_cast<uint4 *>(state) + me * (kParts * kHalfChunks) + lane);
+    const uint32_t put_at = pinned(S::put_address(strip, lane));
+    const uint32_t mine_at = ring + 16 * lane;
+
+    // the fetch stream runs two halves ahead: `ahead` = first vector of the next half to request
+    const uint4 *ahead = pinned(reinterpret_cast<const uint4 *>(x) + me * (kParts * kHalf) + lane);
+    int64_t to_fetch = mine * kParts;
+    uint32_t fill = 0, slot = 0;   // byte offsets of the slot to fill next / to read next
+    int fetch_part = 0;
+    auto next_slot = [](uint32_t v) { return v == 2 * kSlot ? 0u : v + kSlot; };
+    auto fetch = [&]() {
+        if (to_fetch > 0) {
+            copy_async16<0>(mine_at + fill, ahead), copy_async16<512>(mine_at + fill, ahead + Subtile<T>::kVectors);
+            --to_fetch;
+            if (kParts == 1 || fetch_part == 1) ahead += unit_step - (kParts - 1) * kHalf; else ahead += kHalf;
+            fetch_part ^= 1;
+        }
+        copy_async_commit();       // an empty group keeps the wait arithmetic uniform
+        fill = next_slot(fill);
+    };
+    fetch();
+    fetch();
+    for (int64_t u = 0; u < mine; ++u, yl += unit_step, out += nwarps * kParts * kHalfChunks) {
+#pragma unroll
+        for (int part = 0; part < kParts; ++part) {
+            typename Subtile<T>::Raw raw[H];
+            copy_async_wait<1>();
+            raw[0].a = lds128<0>(mine_at + slot), raw[1].a = lds128<512>(mine_at + slot);
+            slot = next_slot(slot);
+            fetch();
+            if (part == 0)
+                forward_half<Op, T, S, kExact, 0, 0, H>(op, scratch, raw, yl, put_at, lane);
+            else
+                forward_half<Op, T, S, kExact, H, H, H>(op, scratch, raw, yl, put_at, lane);
+        }
+        S::flush(strip, out, lane);
+    }
+    copy_async_wait<0>();
+}
+
 template <class Op, typename T, int U, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) forward_tiles_kernel(const T *x, T *y, uint8_t *state,
                                                                 int64_t ntiles, Op op) {
     constexpr int B = Op::kBits;
-    constexpr int kStrip = Stager<T, B, U>::kBytes > Stager<T, B, 1>::kBytes ? Stager<T, B, U>::kBytes
-                                                                              : Stager<T, B, 1>::kBytes;
+    constexpr bool kRing = streams_input<Op, T, U>();
+    constexpr int kStaged = kRing && !Stager<T, B, U>::kTransposed ? U / 2 : U;   // subtiles staged at a time
+    constexpr int kStrip = Stager<T, B, kStaged>::kBytes > Stager<T, B, 1>::kBytes ? Stager<T, B, kStaged>::kBytes
+                                                                                    : Stager<T, B, 1>::kBytes;
     __shared__ alignas(16) uint8_t strips[kWarps][(kStrip + 15) / 16 * 16];
+    __shared__ alignas(16) uint8_t rings[kRing ? kWarps : 1][kRing ? 3 * 1024 : 16];   // cp.async input ring
     __shared__ typename Op::Scratch scratch;
     op.prepare(scratch);
     const uint32_t strip = (uint32_t)__cvta_generic_to_shared(strips[threadIdx.x >> 5]);
-    if (op.exact())
-        forward_loop<Op, T, U, true>(op, scratch, x, y, state, ntiles, strip);
-    else
-        forward_loop<Op, T, U, false>(op, scratch, x, y, state, ntiles, strip);
+    if constexpr (kRing) {
+        const uint32_t ring = (uint32_t)__cvta_generic_to_shared(rings[threadIdx.x >> 5]);
+        if (op.exact())
+            forward_stream<Op, T, true>(op, scratch, x, y, state, ntiles * 2, strip, ring);
+        else
+            forward_stream<Op, T, false>(op, scratch, x, y, state, ntiles * 2, strip, ring);
+    } else {
+        if (op.exact())
+            forward_loop<Op, T, U, true>(op, scratch, x, y, state, ntiles, strip);
+        else
+            forward_loop<Op, T, U, false>(op, scratch, x, y, state, ntiles, strip);
+    }
 }
 
 template <class Op, typename T, int U, int MINB>

@@ -22,6 +22,8 @@ from typing import Literal, Optional
 import torch as T
 import torch.nn.functional as F
 
+from ..fft import dct
+
 __all__ = ('linear_crs', 'linear_grp', 'linear_randomized', 'calc_proj_dim')
 
 MatMulType = Literal['gaussian', 'rademacher', 'dct', 'dft']
@@ -62,10 +64,46 @@ def _sketch_matrix(kind: str, rows: int, cols: int, generator: T.Generator, devi
     if kind == 'rademacher':
         return T.randint(high=2, size=(rows, cols), generator=generator, device=device,
                          dtype=dtype) - 0.5
-    if kind in ('dct', 'dft'):
-        raise NotImplementedError(f"matmul='{kind}' is outside the B200 hot path (SURVEY 2.1 #8); "
-                                  "use 'gaussian' or 'rademacher'.")
     raise ValueError(f'Unexpected matmul type: {kind}.')
+
+
+def _sampled_rows(rows: int, count: int, generator: T.Generator, device) -> T.Tensor:
+    """`rows` token indices drawn uniformly with replacement (reference :114-119, :123-128)."""
+    probas = T.ones(count, device=device)
+    probas /= count
+    return T.multinomial(input=probas, num_samples=rows, replacement=True, generator=generator)
+
+
+def _transform(kind: str, view: T.Tensor, inverse: bool = False) -> T.Tensor:
+    """Orthonormal cosine / Fourier transform along the token axis.  torch.fft has no bf16 / fp16
+    kernels: those inputs are transformed in fp32."""
+    work = view if view.dtype in (T.float32, T.float64) else view.float()
+    if kind == 'dct':
+        return dct(work, dim=0, norm='ortho').to(view.dtype)
+    return (T.fft.ifft if inverse else T.fft.fft)(work, dim=0, norm='ortho')
+
+
+def _project_input(kind: str, view: T.Tensor, rows: int, generator: T.Generator) -> T.Tensor:
+    """What is saved instead of the input (reference forward, :113-146), with the very arithmetic
+    of the reference.  Note its scale for the two transform sketches: rows * tokens, where an
+    unbiased estimate would need tokens / rows -- kept, a drop-in must return what the reference
+    returns (tests/golden/reference_linear.npz pins it); see DESIGN.md section 5."""
+    if kind in ('dct', 'dft'):
+        picked = _sampled_rows(rows, view.shape[0], generator, view.device)
+        return (rows * view.shape[0]) * _transform(kind, view)[picked, ...]
+    proj = _sketch_matrix(kind, rows, view.shape[0], generator, view.device, view.dtype)
+    # E[S^T S] = P I (gaussian) or P/4 I (rademacher): scale so that E[grad_weight] = G^T X
+    if kind == 'gaussian':
+        return (proj @ view) / rows
+    return (proj @ view) * (4 / rows)
+
+
+def _project_grad(kind: str, grad_view: T.Tensor, rows: int, generator: T.Generator, like: T.Tensor) -> T.Tensor:
+    """The same sketch applied to grad_output (reference backward, :178-211)."""
+    if kind in ('dct', 'dft'):
+        picked = _sampled_rows(rows, grad_view.shape[0], generator, grad_view.device)
+        return _transform(kind, grad_view, inverse=True)[picked, :]
+    return _sketch_matrix(kind, rows, grad_view.shape[0], generator, grad_view.device, like.dtype) @ grad_view
 
 
 def _linear_owning_output(input_view: T.Tensor, weight: T.Tensor, bias: Optional[T.Tensor],
@@ -114,18 +152,42 @@ def _draw_stream(generator: T.Generator):
 
 
 class _SharedSketch:
-    """The last sketch taken with ``share_sketch=True``, per device: layers that are fed the very
-    same tensor one after the other (the query / key / value projections of an attention block)
-    reuse one ``S X`` instead of sketching it three times.  Only a weak reference
-    to the input is kept -- the point of the layer is NOT to keep its input alive."""
-    __slots__ = ('input', 'version', 'rows', 'kind', 'projection', 'stream')
+    """A sketch taken with ``share_sketch=True``: layers that are fed the very same tensor one
+    after the other (the query / key / value projections of an attention block) reuse one ``S X``
+    instead of sketching it three times.
 
-    def matches(self, tensor: T.Tensor, rows: int, kind: str) -> bool:
-        return (self.input() is tensor and self.version == tensor._version and self.rows == rows
-                and self.kind == kind)
+    The record hangs off the INPUT TENSOR OBJECT (attribute ``_fewbit_shared_sketch``), so it lives
+    exactly as long as that tensor does -- no process-wide table, nothing that keeps a projection
+    alive after its input is gone, nothing shared between threads that work on different tensors.
+    It is dropped as soon as one of its consumers runs backward: an input that is fed again in a
+    later step (fixed batches, eval followed by train) is sketched afresh, so the sketch noise of
+    successive optimiser steps stays independent."""
+    __slots__ = ('version', 'rows', 'kind', 'projection', 'stream')
+    ATTRIBUTE = '_fewbit_shared_sketch'
+
+    @classmethod
+    def find(cls, tensor: T.Tensor, rows: int, kind: str) -> Optional['_SharedSketch']:
+        record = tensor.__dict__.get(cls.ATTRIBUTE)
+        if (record is not None and record.version == tensor._version and record.rows == rows
+                and record.kind == kind):
+            return record
+        return None
+
+    @classmethod
+    def drop(cls, tensor_ref) -> None:
+        tensor = tensor_ref() if tensor_ref is not None else None
+        if tensor is not None:
+            tensor.__dict__.pop(cls.ATTRIBUTE, None)
 
 
-_SHARED: dict = {}
+def _autocast_operands(input_view: T.Tensor, weight: T.Tensor, bias: Optional[T.Tensor]):
+    """``F.linear`` would be autocast; the ``out=`` product that replaces it is not (and raises on
+    mixed dtypes), so the operands are cast here the way autocast would."""
+    kind = input_view.device.type
+    if T.is_autocast_enabled(kind):
+        dtype = T.get_autocast_dtype(kind)
+        return (input_view.to(dtype), weight.to(dtype), None if bias is None else bias.to(dtype))
+    return input_view, weight, bias
 
 
 class LinearGRPFunc(T.autograd.Function):
@@ -141,76 +203,86 @@ class LinearGRPFunc(T.autograd.Function):
             raise ValueError('Param proj_dim_min should be strictly positive.')
         if proj_dim_min and proj_dim_max and proj_dim_max < proj_dim_min:
             raise ValueError('Param proj_dim_min should be not greater than param proj_dim_max.')
+        if matmul not in ('gaussian', 'rademacher', 'dct', 'dft'):
+            raise ValueError(f'Unexpected matmul type: {matmul}.')
 
         generator = generator or _default_generator(input.device)
         input_view = input.reshape(-1, input.shape[-1])
         proj_features = calc_proj_dim(input_view.shape[0], proj_dim_ratio, proj_dim, proj_dim_max,
                                       proj_dim_min)
+        ctx.proj_features = proj_features
+        ctx.matmul = matmul
+        ctx.stream = ctx.generator_state = ctx.shared_input = None
+        ctx.autocast = (T.is_autocast_enabled(input.device.type), T.get_autocast_dtype(input.device.type))
+        lhs, rhs, offset_term = _autocast_operands(input_view, weight, bias)
 
-        if _native_sketch_available(input_view, matmul) and generator.device.type == 'cuda':
+        if not ctx.needs_input_grad[1]:
+            # frozen weight / inference: nothing will ever read a sketch, so none is taken
+            ctx.save_for_backward(None, weight, bias)
+        elif (proj_features > 0 and _native_sketch_available(input_view, matmul)
+              and generator.device.type == 'cuda'):
             # B200 path: S never exists in memory; (seed, offset) replaces the generator state.
-            shared = _SHARED.get(input.device) if share_sketch else None
-            if shared is not None and shared.matches(input, proj_features, matmul):
+            shared = _SharedSketch.find(input, proj_features, matmul) if share_sketch else None
+            if shared is not None:
                 input_proj, (seed, offset) = shared.projection, shared.stream
             else:
                 seed, offset = _draw_stream(generator)
                 scale = 1.0 / proj_features if matmul == 'gaussian' else 4.0 / proj_features
                 input_proj = _native_sketch(input_view, proj_features, seed, offset, matmul, scale).to(input.dtype)
                 if share_sketch:
-                    shared = _SHARED[input.device] = _SharedSketch()
-                    shared.input, shared.version = weakref.ref(input), input._version
-                    shared.rows, shared.kind = proj_features, matmul
+                    shared = _SharedSketch()
+                    shared.version, shared.rows, shared.kind = input._version, proj_features, matmul
                     shared.projection, shared.stream = input_proj, (seed, offset)
+                    setattr(input, _SharedSketch.ATTRIBUTE, shared)
+            if share_sketch:
+                ctx.shared_input = weakref.ref(input)
             ctx.save_for_backward(input_proj, weight, bias)
-            ctx.proj_features = proj_features
-            ctx.matmul = matmul
             ctx.stream = (seed, offset)
-            return _linear_owning_output(input_view, weight, bias, input.shape)
-
-        generator_state = generator.get_state()
-        ctx.stream = None
-        proj = _sketch_matrix(matmul, proj_features, input_view.shape[0], generator, input.device,
-                              input.dtype)
-        # E[S^T S] = P I (gaussian) or P/4 I (rademacher): scale so that E[grad_weight] = G^T X,
-        # with the very arithmetic of the reference (:137, :146).
-        if matmul == 'gaussian':
-            input_proj = (proj @ input_view) / proj_features
         else:
-            input_proj = (proj @ input_view) * (4 / proj_features)
-        del proj
-
-        ctx.save_for_backward(input_proj, weight, bias)
-        ctx.proj_features = proj_features
-        ctx.matmul = matmul
-        ctx.generator_state = generator_state
-        ctx.generator_device = generator.device
-        return _linear_owning_output(input_view, weight, bias, input.shape)
+            # CPU tensors, the transform sketches, feature counts the TMA cannot address, P = 0
+            # (an empty sketch and a zero weight gradient, as in the reference): PyTorch ops
+            ctx.generator_state = generator.get_state()
+            ctx.generator_device = generator.device
+            ctx.save_for_backward(_project_input(matmul, input_view, proj_features, generator), weight, bias)
+        return _linear_owning_output(lhs, rhs, offset_term, input.shape)
 
     @staticmethod
     def backward(ctx, grad_output):
         input_proj, weight, bias = ctx.saved_tensors
         grad_input = grad_weight = grad_bias = None
-        if ctx.needs_input_grad[0]:
-            grad_input = grad_output @ weight
-        if ctx.needs_input_grad[1] and ctx.stream is not None:
-            grad_view = grad_output.reshape(-1, grad_output.shape[-1])
-            if _native_sketch_available(grad_view, ctx.matmul):
-                grad_proj = _native_sketch(grad_view, ctx.proj_features, *ctx.stream, ctx.matmul, 1.0)
-            else:  # feature count the TMA cannot address: same S, materialised
-                proj = T.ops.fewbit.sketch_matrix(grad_view, ctx.proj_features, grad_view.shape[0],
-                                                  *ctx.stream, SKETCH_KINDS[ctx.matmul])
-                grad_proj = proj.float() @ grad_view.float()
-            # (S G)^T (S X): a small [out, P] x [P, in] product in the layer's own precision
-            grad_weight = grad_proj.to(input_proj.dtype).T @ input_proj
-        elif ctx.needs_input_grad[1]:
-            generator = T.Generator(ctx.generator_device)
-            generator.set_state(ctx.generator_state)
-            grad_view = grad_output.reshape(-1, grad_output.shape[-1])
-            proj = _sketch_matrix(ctx.matmul, ctx.proj_features, grad_view.shape[0], generator,
-                                  grad_output.device, grad_output.dtype)
-            grad_weight = (proj @ grad_view).T @ input_proj
-        if bias is not None and ctx.needs_input_grad[2]:
-            grad_bias = grad_output.reshape(-1, grad_output.shape[-1]).sum(dim=0)
+        enabled, dtype = ctx.autocast
+        with T.autocast(grad_output.device.type, dtype=dtype, enabled=enabled):
+            if ctx.needs_input_grad[0]:
+                grad_input = grad_output @ weight
+            if ctx.needs_input_grad[1] and ctx.stream is not None:
+                _SharedSketch.drop(ctx.shared_input)
+                grad_view = grad_output.reshape(-1, grad_output.shape[-1])
+                if _native_sketch_available(grad_view, ctx.matmul):
+                    grad_proj = _native_sketch(grad_view, ctx.proj_features, *ctx.stream, ctx.matmul, 1.0)
+                else:  # feature count the TMA cannot address: same S, materialised
+                    proj = T.ops.fewbit.sketch_matrix(grad_view, ctx.proj_features, grad_view.shape[0],
+                                                      *ctx.stream, SKETCH_KINDS[ctx.matmul])
+                    grad_proj = proj.float() @ grad_view.float()
+                # (S G)^T (S X): a small [out, P] x [P, in] product in the layer's own precision
+                grad_weight = grad_proj.to(input_proj.dtype).T @ input_proj
+            elif ctx.needs_input_grad[1]:
+                generator = T.Generator(ctx.generator_device)
+                generator.set_state(ctx.generator_state)
+                grad_view = grad_output.reshape(-1, grad_output.shape[-1])
+                grad_proj = _project_grad(ctx.matmul, grad_view, ctx.proj_features, generator, input_proj)
+                if ctx.matmul == 'dft':
+                    # sum_p conj-free product of two spectra; its real part estimates G^T X.  (The
+                    # reference drops the imaginary part of one factor first and then fails on the
+                    # mixed-dtype product, functional/linear.py:213-215.)
+                    grad_weight = (grad_proj.T @ input_proj).real.to(weight.dtype)
+                else:
+                    grad_weight = grad_proj.T @ input_proj
+            if bias is not None and ctx.needs_input_grad[2]:
+                grad_bias = grad_output.reshape(-1, grad_output.shape[-1]).sum(dim=0)
+        if grad_weight is not None and grad_weight.dtype != weight.dtype:
+            grad_weight = grad_weight.to(weight.dtype)
+        if grad_bias is not None and grad_bias.dtype != bias.dtype:
+            grad_bias = grad_bias.to(bias.dtype)
         return (grad_input, grad_weight, grad_bias) + (None, ) * 7
 
 

@@ -177,13 +177,21 @@ def piecewise_backward_host(func, state, gout_host, gin_host, p0=0.0, chunk=0):
 SKETCH_KINDS = ('gaussian', 'rademacher')
 
 
-def sketch_forward(x, rows, seed, offset, kind='gaussian', scale=1.0, stream=None):
-    """x: [tokens, features] bf16 device tensor -> [rows, features] fp32."""
+def sketch_workspace(x, rows):
+    """Scratch buffer fewbit_sketch_forward wants for this shape (split-K partial sums)."""
+    tokens, features = x.shape
+    nbytes = int(lib().fewbit_sketch_workspace_bytes(tokens, features, rows))
+    return torch.empty(max(nbytes, 16), dtype=torch.uint8, device=x.device)
+
+
+def sketch_forward(x, rows, seed, offset, kind='gaussian', scale=1.0, stream=None, out=None, workspace=None):
+    """x: [tokens, features] bf16 device tensor -> [rows, features] fp32.  `out` / `workspace`:
+    preallocated buffers (timing loops that must contain nothing but the kernels)."""
     assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.is_contiguous()
     tokens, features = x.shape
-    out = torch.empty(rows, features, dtype=torch.float32, device=x.device)
-    nbytes = int(lib().fewbit_sketch_workspace_bytes(tokens, features, rows))
-    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=x.device)
+    if out is None:
+        out = torch.empty(rows, features, dtype=torch.float32, device=x.device)
+    ws = workspace if workspace is not None else sketch_workspace(x, rows)
     check(lib().fewbit_sketch_forward(x.data_ptr(), out.data_ptr(), ws.data_ptr(), tokens, features, rows,
                                       SKETCH_KINDS.index(kind), scale, seed, offset, _stream(stream)),
           'fewbit_sketch_forward')

@@ -127,7 +127,8 @@ def main():
     # ---- reference RandomizedLinear on CPU ----------------------------------------
     from fewbit.modules.linear import LinearGRP
     lin = {}
-    for kind in ('gaussian', 'rademacher'):
+    # 'dft' is absent: the reference's backward raises on it (real grad @ complex sketch, :213-215)
+    for kind in ('gaussian', 'rademacher', 'dct'):
         for bias in (False, True):
             torch.manual_seed(42)
             layer = LinearGRP(24, 12, bias, proj_dim=16, matmul=kind)

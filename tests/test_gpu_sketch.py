@@ -161,12 +161,51 @@ def test_layers_fed_the_same_tensor_can_share_one_sketch():
     torch.cuda.synchronize()
     per_sketch = native.lib().fewbit_launch_count() - single
     assert launches == per_sketch, (launches, per_sketch)
+    # the record lives on the input tensor and is gone once a consumer has run backward: the same
+    # tensor fed again (a later step) is sketched afresh, nothing keeps the projection alive
+    assert '_fewbit_shared_sketch' not in hidden.__dict__
+    offset = gen.get_offset()
+    q(hidden), k(hidden)
+    assert gen.get_offset() == offset + 4 and '_fewbit_shared_sketch' in hidden.__dict__
     # a modified or different tensor is not a hit
     offset = gen.get_offset()
-    with torch.no_grad():
-        fresh = hidden.detach().clone()
-        q(fresh)
-        fresh.add_(1.0)
-        k(fresh)
-        v(fresh.clone())
+    fresh = hidden.detach().clone()
+    q(fresh)
+    fresh.add_(1.0)
+    k(fresh)
+    v(fresh.clone())
     assert gen.get_offset() == offset + 12
+    # without a gradient to estimate no sketch is taken at all (inference, frozen weights)
+    offset = gen.get_offset()
+    with torch.no_grad():
+        q(fresh)
+    assert gen.get_offset() == offset
+
+
+def test_single_token_and_frozen_weight_on_cuda():
+    """ADVICE r1: int(0.2 * N) == 0 for N < 5 tokens used to divide by zero on the native path;
+    now an empty sketch and a zero weight gradient (the reference's behaviour)."""
+    layer = fewbit.RandomizedLinear(256, 128, proj_dim_ratio=0.2).to(DEV)
+    x = torch.randn(1, 256, device=DEV, requires_grad=True)
+    y = layer(x)
+    torch.testing.assert_close(y, torch.nn.functional.linear(x, layer.weight, layer.bias))
+    y.sum().backward()
+    assert torch.count_nonzero(layer.weight.grad) == 0 and x.grad is not None
+    layer.weight.requires_grad_(False)
+    before = native.lib().fewbit_launch_count()
+    layer(torch.randn(512, 256, device=DEV, requires_grad=True)).sum().backward()
+    assert native.lib().fewbit_launch_count() == before       # no projection kernel ran
+
+
+@pytest.mark.parametrize('kind', ['dct', 'dft'])
+def test_transform_sketches_run_on_cuda(kind):
+    """The dct / dft sketches are torch.fft compositions on either device (reference
+    fewbit/functional/linear.py:113-132); same estimate as on the CPU for the same sampled rows."""
+    torch.manual_seed(3)
+    layer = fewbit.RandomizedLinear(64, 32, proj_dim=16, matmul=kind, generator=torch.Generator(DEV).manual_seed(11)).to(DEV)
+    x = torch.randn(8, 16, 64, device=DEV, requires_grad=True)
+    y = layer(x)
+    torch.testing.assert_close(y, torch.nn.functional.linear(x, layer.weight, layer.bias), rtol=1e-4, atol=1e-4)
+    y.backward(torch.randn_like(y))
+    assert layer.weight.grad.shape == (32, 64) and layer.weight.grad.dtype == torch.float32
+    assert torch.isfinite(layer.weight.grad).all() and x.grad is not None

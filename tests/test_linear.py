@@ -7,7 +7,7 @@ import fewbit_b200 as fewbit
 from fewbit_b200.functional.linear import calc_proj_dim
 
 
-@pytest.mark.parametrize('kind', ['gaussian', 'rademacher'])
+@pytest.mark.parametrize('kind', ['gaussian', 'rademacher', 'dct'])
 @pytest.mark.parametrize('bias', [False, True])
 def test_bit_exact_with_reference_on_cpu(golden_linear, kind, bias):
     """Same seed -> same sketch -> same y / grad_input / grad_weight / grad_bias as
@@ -26,7 +26,12 @@ def test_bit_exact_with_reference_on_cpu(golden_linear, kind, bias):
     y.backward(g['gy'])
     torch.testing.assert_close(y.detach(), g['y'], rtol=0, atol=0)
     torch.testing.assert_close(x.grad, g['grad_input'], rtol=0, atol=0)
-    torch.testing.assert_close(layer.weight.grad, g['grad_weight'], rtol=0, atol=0)
+    if kind == 'dct':
+        # same sampled rows, same scale (rows * tokens, the reference's); the cosine transform is
+        # this package's own torch.fft composition (fewbit_b200/fft.py): equal to rounding
+        torch.testing.assert_close(layer.weight.grad, g['grad_weight'], rtol=2e-5, atol=2e-5 * g['grad_weight'].abs().max().item())
+    else:
+        torch.testing.assert_close(layer.weight.grad, g['grad_weight'], rtol=0, atol=0)
     if bias:
         torch.testing.assert_close(layer.bias.grad, g['grad_bias'], rtol=0, atol=0)
 
@@ -47,8 +52,8 @@ def test_proj_dim_rules():
         fewbit.LinearGRP(4, 4, proj_dim=2, proj_dim_min=-1)(torch.randn(8, 4))
     with pytest.raises(ValueError):
         fewbit.LinearGRP(4, 4, proj_dim=2, proj_dim_min=5, proj_dim_max=3)(torch.randn(8, 4))
-    with pytest.raises(NotImplementedError):
-        fewbit.LinearGRP(4, 4, proj_dim=2, matmul='dct')(torch.randn(8, 4))
+    with pytest.raises(ValueError):
+        fewbit.LinearGRP(4, 4, proj_dim=2, matmul='hadamard')(torch.randn(8, 4))
 
 
 def test_forward_is_exact():
@@ -89,6 +94,68 @@ def test_weight_gradient_is_unbiased(kind):
     assert (torch.linalg.norm(gb - ref.bias.grad) / torch.linalg.norm(ref.bias.grad)).item() < 1e-6
     err = torch.linalg.norm(acc / repeats - ref.weight.grad) / torch.linalg.norm(ref.weight.grad)
     assert err.item() < 0.2
+
+
+@pytest.mark.parametrize('kind', ['dct', 'dft'])
+def test_transform_sketches_estimate_the_weight_gradient(kind):
+    """Rows of the orthonormal cosine / Fourier transform of the token axis, sampled with
+    replacement (reference fewbit/functional/linear.py:113-132, 178-205).  Up to the reference's
+    scale -- rows * tokens where tokens / rows would be unbiased, i.e. rows^2 too large, kept for
+    parity -- the mean over many draws approaches G^T X.  The reference itself cannot run 'dft'
+    (its backward multiplies a real by a complex matrix and raises); here the estimate is the real
+    part of the product of the two spectra."""
+    torch.manual_seed(42)
+    rows = 32
+    layer = fewbit.LinearGRP(24, 12, True, proj_dim=rows, matmul=kind)
+    x = torch.randn(64, 24, requires_grad=True)
+    gy = torch.randn(64, 12)
+    exact = gy.T @ x.detach()
+    acc = torch.zeros_like(layer.weight)
+    repeats = 1024
+    for _ in range(repeats):
+        layer.zero_grad()
+        layer(x).backward(gy)
+        assert layer.weight.grad.dtype == torch.float32
+        acc += layer.weight.grad
+    err = torch.linalg.norm(acc / repeats / rows ** 2 - exact) / torch.linalg.norm(exact)
+    assert err.item() < 0.15, err.item()
+    torch.testing.assert_close(layer.bias.grad, gy.sum(0))
+
+
+def test_no_tokens_to_sketch_and_frozen_weights():
+    """int(ratio * N) == 0 (a single token at ratio 0.2) is an empty sketch and a zero weight
+    gradient, as in the reference; a layer whose weight needs no gradient takes no sketch at all."""
+    layer = fewbit.LinearGRP(8, 4, True, proj_dim_ratio=0.2)
+    x = torch.randn(1, 8, requires_grad=True)
+    y = layer(x)
+    torch.testing.assert_close(y, torch.nn.functional.linear(x, layer.weight, layer.bias))
+    y.sum().backward()
+    assert torch.count_nonzero(layer.weight.grad) == 0 and layer.weight.grad.shape == (4, 8)
+    torch.testing.assert_close(x.grad, layer.weight.sum(0, keepdim=True))
+    frozen = fewbit.LinearGRP(8, 4, True, proj_dim=2)
+    frozen.weight.requires_grad_(False)
+    state = torch.get_rng_state()
+    z = frozen(torch.randn(16, 8, requires_grad=True) * 1.0)
+    z.sum().backward()
+    assert frozen.weight.grad is None and frozen.bias.grad is not None
+    with torch.no_grad():
+        before = torch.get_rng_state()
+        frozen(torch.randn(16, 8))
+    del state, before
+
+
+def test_autocast_matches_linear():
+    """Under autocast the layer computes what F.linear computes (bf16 operands), although its
+    forward product is an out= call that autocast does not intercept."""
+    layer = fewbit.LinearGRP(16, 8, True, proj_dim=8)
+    x = torch.randn(4, 6, 16, requires_grad=True)
+    with torch.autocast('cpu', dtype=torch.bfloat16):
+        y = layer(x)
+        expect = torch.nn.functional.linear(x, layer.weight, layer.bias)
+    assert y.dtype == expect.dtype == torch.bfloat16
+    torch.testing.assert_close(y, expect)
+    y.float().sum().backward()
+    assert layer.weight.grad.dtype == torch.float32 and x.grad.dtype == torch.float32
 
 
 def test_user_generator_is_honoured_and_replayed():

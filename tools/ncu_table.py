@@ -43,6 +43,28 @@ def short(name):
     return name.replace('void ', '')[:90]
 
 
+def traffic_key(name):
+    """bench.py's name of a profiled kernel (benchmarks/profile_kernels.py launches them at the
+    bench's sizes), or None."""
+    name = name.replace('fewbit::', '')
+    tag = 'bf16' if '__nv_bfloat16' in name else 'f32'
+    m = re.search(r'MaskOp<(\w+?)Fn>', name)
+    if m and 'forward_tiles' in name:
+        return {'Relu': 'relu', 'LeakyRelu': 'leaky_relu', 'Hardtanh': 'hardtanh'}.get(m.group(1), m.group(1).lower()) + \
+            ('_forward' if tag == 'bf16' else '_f32_forward')
+    if 'MaskFactorOp' in name and 'backward_tiles' in name:
+        return 'relu_backward' if tag == 'bf16' else 'relu_f32_backward'     # one kernel serves every 1-bit backward
+    m = re.search(r'QuantizeOp<(\w+?)Fn, (?:__nv_bfloat16|float), (\d)>', name)
+    if m and 'forward_tiles' in name:
+        return f'{m.group(1).lower()}{m.group(2)}_{tag}_forward'
+    m = re.search(r'LevelsOp<(?:__nv_bfloat16|float), (\d)>', name)
+    if m and 'backward_tiles' in name:
+        return f'levels{m.group(1)}_{tag}_backward'
+    if 'sketch_kernel' in name:
+        return 'sketch_kernel'
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('csv')
@@ -68,8 +90,8 @@ def main():
             cells.append(f'{v:.1f}' if abs(v) < 1e4 else f'{v:.0f}')
         name = r[col['Kernel Name']]
         print(f'| `{short(name)}` | ' + ' | '.join(cells) + ' |')
-        if 'MaskOp<ReluFn>' in name or 'MaskOp<fewbit::ReluFn>' in name or 'MaskFactorOp' in name:
-            key = 'relu_forward' if 'forward' in name else 'relu_backward'
+        key = traffic_key(name)
+        if key:
             total = sum(number(r[col[m]]) * UNIT.get(units[col[m]], 1.0) * 1e6
                         for m in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
             traffic.setdefault(key, total)

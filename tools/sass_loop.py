@@ -44,7 +44,7 @@ def main():
     addr = {a: i for i, (a, _) in enumerate(body)}
     # every innermost backward branch that spans a 128-bit global load is a candidate; the main
     # loop is the largest one that does not call out of line (the exact-search loop does)
-    loads = [i for i, (_, ins) in enumerate(body) if re.search(r'LDG\.E(\.NA)?\.128', ins)]
+    loads = [i for i, (_, ins) in enumerate(body) if re.search(r'LDG\.E(\.NA)?\.128|LDGSTS', ins)]
     loops = {}
     for first in loads:
         best = None
