@@ -456,7 +456,7 @@ def side_measurements(dev, peak, traffic_table):
     """Not part of the headline: the other kernels of the path, each timed alone (N = 1 only).
 
     3-bit GELU on 128 x 128 x 3072 (configs[0] / [2]), fp32 and bf16, forward and backward: median of
-    20 launches; before every launch the L2 is flushed by READING a 256 MiB buffer, so the inputs
+    20 launches; before every launch the L2 is flushed by READING a 1 GiB buffer, so the inputs
     come from HBM and the L2 holds clean lines (flushing by writing would leave 126 MB of dirty
     lines for the timed kernel to evict; back-to-back launches would leave its own ~50 MB of
     write-back in L2 -- the two differ by 5-10 % on a 100-200 MB tensor).
@@ -469,13 +469,14 @@ def side_measurements(dev, peak, traffic_table):
     from fewbit_b200.functional import store
     out, rooflines = {}, []
     n = 128 * 128 * 3072
-    flush = torch.ones(256 << 18, dtype=torch.float32, device=dev)     # 256 MiB
+    flush = torch.ones(256 << 20, dtype=torch.float32, device=dev)     # 1 GiB: read before every timed launch
     sink = torch.zeros((), dtype=torch.float32, device=dev)
 
     def timed(fn, reps=25, skip=5):
         ts = []
         for it in range(reps):
-            sink.copy_(flush.sum())                                    # read 256 MiB > L2
+            sink.copy_(flush.sum())                                    # read 1 GiB >> L2; ~170 us of GPU time, during
+                                                                       # which the timed launch is already enqueued
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); fn(); b.record()
             torch.cuda.synchronize()
@@ -483,7 +484,7 @@ def side_measurements(dev, peak, traffic_table):
                 ts.append(a.elapsed_time(b))
         return statistics.median(ts)
 
-    where = '128x128x3072 elements, median of 20 single launches, L2 flushed by reading 256 MiB before each'
+    where = '128x128x3072 elements, median of 20 single launches, L2 flushed by reading 1 GiB before each'
     for tag, dtype, es in (('f32', torch.float32, 4), ('bf16', torch.bfloat16, 2)):
         borders, levels = store.get('gelu', 3, dev, dtype)
         bounds = borders[1:-1].contiguous()

@@ -17,6 +17,7 @@ FEWBIT_DECLARE(tanhshrink)
 #undef FEWBIT_DECLARE
 
 cudaError_t launch_levels_backward(const BackwardArgs &);
+cudaError_t launch_custom_forward(const ForwardArgs &, const void *levels, int nlevels);
 cudaError_t launch_piecewise_forward(int func, const ForwardArgs &);
 cudaError_t launch_piecewise_backward(int func, const BackwardArgs &);
 cudaError_t launch_deflate(const int32_t *, uint8_t *, int64_t, int, cudaStream_t);
@@ -69,15 +70,12 @@ struct HostPipeline {
     cudaStream_t streams[kSlots] = {};
     void *in[kSlots] = {}, *out[kSlots] = {};
     size_t capacity = 0;
-    int device = -1;
 
+    // Called with `mu` held and this pipeline's device current.
     cudaError_t ensure(size_t bytes) {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
-        if (dev == device && bytes <= capacity) return cudaSuccess;
+        if (bytes <= capacity) return cudaSuccess;
         release();
-        device = dev;
+        cudaError_t e;
         for (int i = 0; i < kSlots; ++i) {
             if ((e = cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
             if ((e = cudaMalloc(&in[i], bytes)) != cudaSuccess) return e;
@@ -96,10 +94,37 @@ struct HostPipeline {
         }
         capacity = 0;
     }
+    // Nothing may still be reading or writing the caller's host buffers when a *_host call returns,
+    // whether it succeeded or not.
+    cudaError_t drain() {
+        cudaError_t first = cudaSuccess;
+        for (int i = 0; i < kSlots; ++i)
+            if (streams[i]) {
+                const cudaError_t e = cudaStreamSynchronize(streams[i]);
+                if (first == cudaSuccess) first = e;
+            }
+        return first;
+    }
 };
-static HostPipeline g_pipe;
+
+// One pipeline per device (staging buffers and streams belong to a device); calls for different
+// devices do not serialise against each other, calls for the same device do.
+static HostPipeline *pipeline_of_current_device(cudaError_t *err) {
+    static HostPipeline pipes[64];
+    int dev = 0;
+    *err = cudaGetDevice(&dev);
+    if (*err != cudaSuccess) return nullptr;
+    if (dev < 0 || dev >= 64) {
+        *err = cudaErrorInvalidDevice;
+        return nullptr;
+    }
+    return &pipes[dev];
+}
 
 // `enqueue(dev_in, dev_out, first_elem, count, stream)` launches the kernel for one chunk.
+// The ring streams are private and non-blocking: the device state buffer and the tables are read
+// and written on them with no ordering against the caller's own streams, so the caller must not
+// have work in flight on those buffers (see include/fewbit_b200.h).
 template <class Enqueue>
 static int run_host_pipeline(int dtype, const void *src_host, void *dst_host, int64_t n,
                              int64_t chunk_elems, Enqueue enqueue) {
@@ -108,26 +133,32 @@ static int run_host_pipeline(int dtype, const void *src_host, void *dst_host, in
     if (chunk_elems <= 0) chunk_elems = (int64_t)1 << 24;        // 16 Mi elements
     chunk_elems = std::max<int64_t>(2048, (chunk_elems / 2048) * 2048);  // whole warp tiles, 16 B state
     chunk_elems = std::min<int64_t>(chunk_elems, ((n + 2047) / 2048) * 2048);
-    std::lock_guard<std::mutex> lock(g_pipe.mu);
-    cudaError_t e = g_pipe.ensure((size_t)chunk_elems * es);
-    if (e != cudaSuccess) return (int)e;
-    int slot = 0;
-    for (int64_t first = 0; first < n; first += chunk_elems, slot = (slot + 1) % HostPipeline::kSlots) {
-        const int64_t count = std::min(chunk_elems, n - first);
-        cudaStream_t s = g_pipe.streams[slot];
-        // the slot's previous D2H must be done before its buffers are reused: same stream -> ordered
-        e = cudaMemcpyAsync(g_pipe.in[slot], (const char *)src_host + first * es, (size_t)count * es,
-                            cudaMemcpyHostToDevice, s);
-        if (e != cudaSuccess) return (int)e;
-        int st = enqueue(g_pipe.in[slot], g_pipe.out[slot], first, count, s);
-        if (st != FEWBIT_OK) return st;
-        e = cudaMemcpyAsync((char *)dst_host + first * es, g_pipe.out[slot], (size_t)count * es,
-                            cudaMemcpyDeviceToHost, s);
-        if (e != cudaSuccess) return (int)e;
+    cudaError_t e = cudaSuccess;
+    HostPipeline *pipe = pipeline_of_current_device(&e);
+    if (!pipe) return (int)e;
+    std::lock_guard<std::mutex> lock(pipe->mu);
+    if ((e = pipe->ensure((size_t)chunk_elems * es)) != cudaSuccess) {
+        pipe->release();
+        return (int)e;
     }
-    for (int i = 0; i < HostPipeline::kSlots; ++i)
-        if ((e = cudaStreamSynchronize(g_pipe.streams[i])) != cudaSuccess) return (int)e;
-    return FEWBIT_OK;
+    int status = FEWBIT_OK, slot = 0;
+    for (int64_t first = 0; first < n && status == FEWBIT_OK;
+         first += chunk_elems, slot = (slot + 1) % HostPipeline::kSlots) {
+        const int64_t count = std::min(chunk_elems, n - first);
+        cudaStream_t s = pipe->streams[slot];
+        // the slot's previous D2H must be done before its buffers are reused: same stream -> ordered
+        e = cudaMemcpyAsync(pipe->in[slot], (const char *)src_host + first * es, (size_t)count * es,
+                            cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) { status = (int)e; break; }
+        status = enqueue(pipe->in[slot], pipe->out[slot], first, count, s);
+        if (status != FEWBIT_OK) break;
+        e = cudaMemcpyAsync((char *)dst_host + first * es, pipe->out[slot], (size_t)count * es,
+                            cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) status = (int)e;
+    }
+    e = pipe->drain();        // also on the error path: earlier chunks are still in flight
+    if (status == FEWBIT_OK && e != cudaSuccess) status = (int)e;
+    return status;
 }
 
 }  // namespace fewbit
@@ -170,6 +201,18 @@ int fewbit_stepwise_forward(int func, int dtype, const void *x, void *y, uint8_t
     if (nbounds > 0 && !bounds) return FEWBIT_EINVAL;
     ForwardArgs a{dtype, x, y, state, n, bits, bounds, nbounds, p0, p1, (cudaStream_t)stream};
     return (int)kContinuous[func](a);
+}
+
+int fewbit_stepwise_custom_forward(int dtype, const void *x, void *y, uint8_t *state, int64_t n, int bits,
+                                   const void *bounds, int nbounds, const void *levels, int nlevels,
+                                   double anchor, void *stream) {
+    if (bits < 1 || bits > 8 || nbounds < 0 || nbounds > (1 << bits) - 1 || nlevels != nbounds + 1)
+        return FEWBIT_EINVAL;
+    if (int st = check_common(dtype, x, y, state, n)) return st;
+    if (n == 0) return FEWBIT_OK;
+    if ((nbounds > 0 && !bounds) || !levels) return FEWBIT_EINVAL;
+    ForwardArgs a{dtype, x, y, state, n, bits, bounds, nbounds, anchor, 0.0, (cudaStream_t)stream};
+    return (int)launch_custom_forward(a, levels, nlevels);
 }
 
 int fewbit_stepwise_backward(int dtype, const uint8_t *state, const void *gout, void *gin, int64_t n,

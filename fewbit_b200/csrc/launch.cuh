@@ -2,12 +2,13 @@
 #pragma once
 
 #include <algorithm>
+#include <atomic>
 #include <type_traits>
 #include <cstdlib>
 
 #include "ops.cuh"
 
-// Tile configuration per kernel class, from the sweep in profiles/r01_tuning_sweep.md
+// Tile configuration per kernel class, from the sweeps in profiles/r01_sweep_{a,b,final}.txt
 // (B200, GB/s of algorithmic bytes; torch's copy kernel reaches 6520 on the same box):
 //   light kernels (1-bit masks, every backward): two LDG.128 in flight per lane and no register
 //     cap -> 6.2-6.3 TB/s; four loads or a tighter register budget cost 5-7 %.
@@ -94,8 +95,10 @@ template <class Op, typename T> struct TileConfig {
 // Resident CTAs per SM for `kernel` (occupancy API, cached per instantiation), overridable
 // with FEWBIT_B200_CTAS_PER_SM for tuning runs.
 template <auto kernel> int resident_ctas(int most) {
-    static int cached = 0;
-    if (cached == 0) {
+    // the answer depends on the kernel and the architecture only (sm_100a everywhere): caching it
+    // per instantiation, not per device, is enough; a racing first call computes the same value
+    static std::atomic<int> cached{0};
+    if (cached.load(std::memory_order_relaxed) == 0) {
         int blocks = 1;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, kThreads, 0) !=
                 cudaSuccess ||
@@ -106,9 +109,9 @@ template <auto kernel> int resident_ctas(int most) {
             int v = std::atoi(env);
             if (v > 0) blocks = std::min(blocks, v);
         }
-        cached = blocks;
+        cached.store(blocks, std::memory_order_relaxed);
     }
-    return cached;
+    return cached.load(std::memory_order_relaxed);
 }
 
 template <typename T> bool vector_aligned(const void *a, const void *b, const void *c) {

@@ -390,25 +390,23 @@ template <class L> __device__ __forceinline__ L expm1(L z) {
     return if_less(abs_(z), lane<L>(0.001953125f), fma_(mul_(z, lane<L>(0.5f)), z, z),
                    add_(exp(z), lane<L>(-1.0f)));
 }
-// tanh away from zero: sign(x) (1 - 2/(1 + e^{2|x|}))
+// tanh(x) = 1 - 2 / (1 + e^{2x}) for either sign: e^{2x} = inf gives 1, e^{2x} = 0 gives -1, NaN stays
+// NaN; no absolute value, no copysign.  Near zero the subtraction cancels (absolute error ~1e-7):
+// below 2^-5 the result is x itself (tanh x = x (1 - x^2/3 ..), x^2/3 < 2^-11.5, far inside half a
+// bf16 ulp), at 2^-5 the cancellation costs 3e-6 relative.
 template <class L> __device__ __forceinline__ L tanh_big(L x) {
-    const L e = ex2_(mul_(abs_(x), lane<L>(2.0f * kLog2e)));
-    return copysign_(fma_(rcp_(add_(e, lane<L>(1.0f))), lane<L>(-2.0f), lane<L>(1.0f)), x);
+    const L e = ex2_(mul_(x, lane<L>(2.0f * kLog2e)));
+    return fma_(rcp_(add_(e, lane<L>(1.0f))), lane<L>(-2.0f), lane<L>(1.0f));
 }
-// tanh: odd polynomial below 1/4 (relative error 3e-7), the form above elsewhere.
 template <class L> __device__ __forceinline__ L tanh(L x) {
-    const L x2 = mul_(x, x);
-    L p = fma_(x2, lane<L>(-0.05396825397f), lane<L>(0.13333333333f));
-    p = fma_(x2, p, lane<L>(-0.33333333333f));
-    p = fma_(x2, p, lane<L>(1.0f));
-    return if_less(abs_(x), lane<L>(0.25f), mul_(x, p), tanh_big(x));
+    return if_less(abs_(x), lane<L>(0.03125f), x, tanh_big(x));
 }
-// x - tanh(x) cancels below 1/4: the series x^3 (1/3 - 2 x^2/15 + 17 x^4/315) there.
+// x - tanh(x) cancels near zero: below 1/8 the series x^3 (1/3 - 2 x^2/15) (next term 17 x^7/315:
+// 2e-5 relative at 1/8); above, the subtraction keeps 1e-7 / (x^3/3) < 2e-4 relative.
 template <class L> __device__ __forceinline__ L tanhshrink(L x) {
     const L x2 = mul_(x, x);
-    L p = fma_(x2, lane<L>(0.05396825397f), lane<L>(-0.13333333333f));
-    p = fma_(x2, p, lane<L>(0.33333333333f));
-    return if_less(abs_(x), lane<L>(0.25f), mul_(mul_(x, x2), p), add_(x, neg_(tanh_big(x))));
+    const L p = fma_(x2, lane<L>(-0.13333333333f), lane<L>(0.33333333333f));
+    return if_less(abs_(x), lane<L>(0.125f), mul_(mul_(x, x2), p), add_(x, neg_(tanh_big(x))));
 }
 template <class L> __device__ __forceinline__ L sigmoid(L x) { return rcp_(add_(exp_neg(x), lane<L>(1.0f))); }
 template <class L> __device__ __forceinline__ L silu(L x) { return mul_(x, sigmoid(x)); }
@@ -598,6 +596,11 @@ struct GeluFn {  // codec.cu:539-544 (x * normcdf(x))
 struct HardswishFn {  // codec.cu:546-564
     __host__ HardswishFn(double, double) {}
     template <typename T> __device__ __forceinline__ float eval(float x) const {
+        // bf16: x * sat(x/6 + 1/2) -- the clamp rides on the multiply-add (FFMA.SAT, FMA pipe);
+        // min/max cost two ALU-pipe ops per element, and the ALU pipe is what bounds this kernel
+        // (ncu: 68 % busy).  Same value as ATen's expression up to the rounding of x/6 + 1/2, far
+        // below bf16 resolution; NaN and infinities behave alike (-inf * 0 = NaN in both).
+        if constexpr (sizeof(T) == 2) return x * __saturatef(fmaf(x, 1.0f / 6.0f, 0.5f));
         return x * fminf(fmaxf(x + 3.0f, 0.0f), 6.0f) * (1.0f / 6.0f);
     }
 };
@@ -750,6 +753,92 @@ template <class Fn, typename T, int B> struct QuantizeOp {
         } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = fn.template eval<T>(v[j]);
+        }
+    }
+};
+
+// Forward op of the custom-table operator `stepwise` (reference schema fewbit/fewbit.cc:37, module
+// fewbit/modules/activations.py:97-134; the reference declares it and ships no kernel).  The
+// table IS the function: levels are the slopes of a continuous piecewise-linear activation with
+// kinks at the borders, anchored at F(anchor) = 0,
+//     F(x) = levels[k] * (x - bounds[k-1]) + F(bounds[k-1])   for bounds[k-1] < x <= bounds[k],
+// so that the backward pass -- levels[code] * grad, the shared kernel -- is its exact derivative.
+// y = fma(levels[code], x, intercept[code]) with the intercepts built per block from a prefix sum
+// (in double) over the pieces.
+template <typename T, int B> struct IntegralOp {
+    static constexpr int kBits = B;
+    static constexpr bool kHeavy = true;
+    static constexpr bool kStreamInput = false;   // its tables leave no room for the input ring at 8 bits
+    static constexpr int kLevels = 1 << B;
+    struct Scratch {
+        typename Bucketizer<T, B>::Scratch bucket;
+        float slope[kLevels], intercept[kLevels];
+        double reach[kLevels];      // reach[k] = F~(bounds[k]) with F~(bounds[0]) = 0
+    };
+    Bucketizer<T, B> bucket;
+    const T *levels;
+    int nlevels;
+    float anchor;
+
+    __device__ __forceinline__ void prepare(Scratch &s) {
+        const int nb = bucket.nbounds, t = threadIdx.x;
+        // piece k (1 <= k < nb) spans (bounds[k-1], bounds[k]]: inclusive scan of its rise
+        for (int k = t; k < kLevels; k += blockDim.x) {
+            s.slope[k] = k < nlevels ? to_float<T>(levels[k]) : 0.0f;
+            s.reach[k] = (k >= 1 && k < nb)
+                             ? (double)to_float<T>(levels[k]) *
+                                   ((double)to_float<T>(bucket.bounds[k]) - (double)to_float<T>(bucket.bounds[k - 1]))
+                             : 0.0;
+        }
+        __syncthreads();
+        for (int step = 1; step < kLevels; step <<= 1) {
+            double add[(kLevels + kThreads - 1) / kThreads];
+#pragma unroll
+            for (int i = 0; i < (kLevels + kThreads - 1) / kThreads; ++i) {
+                const int k = t + i * kThreads;
+                add[i] = (k < kLevels && k >= step) ? s.reach[k - step] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < (kLevels + kThreads - 1) / kThreads; ++i) {
+                const int k = t + i * kThreads;
+                if (k < kLevels) s.reach[k] += add[i];
+            }
+            __syncthreads();
+        }
+        // F~ at the anchor: its piece is found by the reference's own search (first border not below it)
+        int piece = 0;
+        while (piece < nb && to_float<T>(bucket.bounds[piece]) < anchor) ++piece;
+        double at_anchor = 0.0;
+        if (nb > 0) {
+            const int left = piece == 0 ? 0 : piece - 1;   // F~ is known at bounds[left]
+            at_anchor = s.reach[left] + (double)s.slope[piece] * ((double)anchor - (double)to_float<T>(bucket.bounds[left]));
+        } else {
+            at_anchor = (double)s.slope[0] * (double)anchor;
+        }
+        for (int k = t; k < kLevels; k += blockDim.x) {
+            double c;
+            if (nb == 0) {
+                c = 0.0;
+            } else {
+                const int left = k == 0 ? 0 : (k - 1 < nb ? k - 1 : nb - 1);
+                c = s.reach[left] - (double)s.slope[k] * (double)to_float<T>(bucket.bounds[left]);
+            }
+            s.intercept[k] = (float)(c - at_anchor);
+        }
+        bucket.prepare(s.bucket);      // ends with a block-wide barrier
+    }
+    __device__ __forceinline__ bool exact() const {
+        if constexpr (Bucketizer<T, B>::kMayCrowd) return bucket.crowded;
+        return false;
+    }
+    template <bool kExact>
+    __device__ __forceinline__ void apply(const Scratch &s, float (&v)[8], uint32_t (&half)[2]) const {
+        bucket.template lookup<kExact>(s.bucket, v, half);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t code = (half[j >> 2] >> (B * (j & 3))) & (kLevels - 1);
+            v[j] = fmaf(s.slope[code], v[j], s.intercept[code]);
         }
     }
 };

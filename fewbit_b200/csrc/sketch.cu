@@ -698,14 +698,15 @@ using EncodeTiled = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t,
                                  CUtensorMapFloatOOBfill);
 
 static EncodeTiled encode_tiled() {
-    static EncodeTiled fn = nullptr;
-    if (!fn) {
+    // a process-wide driver entry point; C++11 makes the one-time initialisation thread-safe
+    static const EncodeTiled fn = [] {
         void *ptr = nullptr;
         cudaDriverEntryPointQueryResult status;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &status) == cudaSuccess &&
             status == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiled>(ptr);
-    }
+            return reinterpret_cast<EncodeTiled>(ptr);
+        return static_cast<EncodeTiled>(nullptr);
+    }();
     return fn;
 }
 

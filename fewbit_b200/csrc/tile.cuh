@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace fewbit {
 
 constexpr int kThreads = 256;
@@ -27,7 +29,7 @@ constexpr int kSubtile = 256;  // elements per warp per round of 128-bit loads
 // ---------------------------------------------------------------- global memory I/O ----
 
 // Tuning knobs (benchmarks/sweep.py builds variants with -D...): cache policy of the streaming
-// loads / stores (measured on B200: no effect, profiles/r01_tuning_sweep.md).
+// loads / stores (measured on B200: no effect, profiles/r01_sweep_a.txt).
 #ifndef FEWBIT_LD_MODE
 #define FEWBIT_LD_MODE 1  // 0: ld.global   1: ld.global.L1::no_allocate   2: ld.global.cs
 #endif
@@ -517,8 +519,10 @@ __device__ __forceinline__ void forward_loop(const Op &op, const typename Op::Sc
 }
 
 // Which forward kernels stream their input through the cp.async ring (forward_stream below).
+template <class Op, typename = void> struct wants_stream : std::true_type {};
+template <class Op> struct wants_stream<Op, std::enable_if_t<!Op::kStreamInput>> : std::false_type {};
 template <class Op, typename T, int U> constexpr bool streams_input() {
-    return Op::kHeavy && sizeof(T) == 2 && U == 4 && FEWBIT_PREFETCH == 2;
+    return Op::kHeavy && wants_stream<Op>::value && sizeof(T) == 2 && U == 4 && FEWBIT_PREFETCH == 2;
 }
 
 // The math-heavy bf16 forward kernels: the same work, streamed.
@@ -537,64 +541,84 @@ template <class Op, typename T, int U> constexpr bool streams_input() {
 // warp u mod nwarps, so the grid still sweeps memory as one window); warps differ by at most one
 // unit, i.e. 512 elements: with ~20 halves per warp on a 100 MB tensor, dealing whole tiles and
 // mopping up with unpipelined single subtiles cost ~10 % in the tail.
-template <class Op, typename T, bool kExact>
-__device__ __forceinline__ void forward_stream(const Op &op, const typename Op::Scratch &scratch, const T *x, T *y,
-                                               uint8_t *state, int64_t nhalves, uint32_t strip, uint32_t ring) {
-    constexpr int B = Op::kBits, H = 2;
-    constexpr bool kWhole = Stager<T, B, 2 * H>::kTransposed;      // unit = tile (two halves)
-    constexpr int kParts = kWhole ? 2 : 1;
+template <class Op, typename T> struct ForwardStream {
+    static constexpr int B = Op::kBits, H = 2;
+    static constexpr bool kWhole = Stager<T, B, 2 * H>::kTransposed;      // unit = tile (two halves)
+    static constexpr int kParts = kWhole ? 2 : 1;
     using S = Stager<T, B, kParts * H>;
-    constexpr int kHalf = H * Subtile<T>::kVectors;                // 128-bit vectors per half
-    constexpr int kHalfChunks = H * subtile_bytes<B>() / 16;       // 16-byte chunks of packed state per half
-    constexpr int kSlot = H * 512;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t nwarps = (int64_t)gridDim.x * kWarps;
-    const int64_t me = (int64_t)blockIdx.x * kWarps + warp;
-    const int64_t nunits = nhalves / kParts;
-    if (me >= nunits) return;
-    const int64_t mine = (nunits - me + nwarps - 1) / nwarps;      // units of this warp
-    const int64_t unit_step = nwarps * kParts * kHalf;             // vectors from one unit to the next
+    static constexpr int kHalf = H * Subtile<T>::kVectors;                // 128-bit vectors per half
+    static constexpr int kHalfChunks = H * subtile_bytes<B>() / 16;       // 16-byte chunks of packed state per half
+    static constexpr uint32_t kSlot = H * 512;
 
-    uint4 *yl = pinned(reinterpret_cast<uint4 *>(y) + me * (kParts * kHalf) + lane);
-    uint4 *out = pinned(reinterpret_cast<uint4 *>(state) + me * (kParts * kHalfChunks) + lane);
-    const uint32_t put_at = pinned(S::put_address(strip, lane));
-    const uint32_t mine_at = ring + 16 * lane;
+    int lane;
+    int64_t nwarps, me;
+    int mine;                 // units of this warp (0: nothing to do)
+    uint32_t ring_at;         // this lane's 16 bytes of slot 0
+    const uint4 *ahead;       // first vector of the next half to request: the fetch stream runs two halves ahead
+    int to_fetch;
+    uint32_t fill, slot;      // byte offsets of the slot to fill next / to read next
+    int fetch_part;
 
-    // the fetch stream runs two halves ahead: `ahead` = first vector of the next half to request
-    const uint4 *ahead = pinned(reinterpret_cast<const uint4 *>(x) + me * (kParts * kHalf) + lane);
-    int64_t to_fetch = mine * kParts;
-    uint32_t fill = 0, slot = 0;   // byte offsets of the slot to fill next / to read next
-    int fetch_part = 0;
-    auto next_slot = [](uint32_t v) { return v == 2 * kSlot ? 0u : v + kSlot; };
-    auto fetch = [&]() {
+    static __device__ __forceinline__ uint32_t next_slot(uint32_t v) { return v == 2 * kSlot ? 0u : v + kSlot; }
+
+    __device__ __forceinline__ void fetch() {
         if (to_fetch > 0) {
-            copy_async16<0>(mine_at + fill, ahead), copy_async16<512>(mine_at + fill, ahead + Subtile<T>::kVectors);
+            copy_async16<0>(ring_at + fill, ahead), copy_async16<512>(ring_at + fill, ahead + Subtile<T>::kVectors);
             --to_fetch;
-            if (kParts == 1 || fetch_part == 1) ahead += unit_step - (kParts - 1) * kHalf; else ahead += kHalf;
+            if (kParts == 1 || fetch_part == 1)
+                ahead += nwarps * (kParts * kHalf) - (kParts - 1) * kHalf;
+            else
+                ahead += kHalf;
             fetch_part ^= 1;
         }
         copy_async_commit();       // an empty group keeps the wait arithmetic uniform
-        fill = next_slot(fill);
-    };
-    fetch();
-    fetch();
-    for (int64_t u = 0; u < mine; ++u, yl += unit_step, out += nwarps * kParts * kHalfChunks) {
-#pragma unroll
-        for (int part = 0; part < kParts; ++part) {
-            typename Subtile<T>::Raw raw[H];
-            copy_async_wait<1>();
-            raw[0].a = lds128<0>(mine_at + slot), raw[1].a = lds128<512>(mine_at + slot);
-            slot = next_slot(slot);
-            fetch();
-            if (part == 0)
-                forward_half<Op, T, S, kExact, 0, 0, H>(op, scratch, raw, yl, put_at, lane);
-            else
-                forward_half<Op, T, S, kExact, H, H, H>(op, scratch, raw, yl, put_at, lane);
-        }
-        S::flush(strip, out, lane);
     }
-    copy_async_wait<0>();
-}
+
+    // Before the operator builds its tables: the first two halves are already on their way.
+    __device__ __forceinline__ void start(const T *x, int64_t nhalves, uint32_t ring) {
+        lane = threadIdx.x & 31;
+        nwarps = (int64_t)gridDim.x * kWarps;
+        me = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+        const int64_t nunits = nhalves / kParts;
+        mine = me < nunits ? (int)((nunits - me + nwarps - 1) / nwarps) : 0;
+        ring_at = ring + 16 * lane;
+        ahead = reinterpret_cast<const uint4 *>(x) + me * (kParts * kHalf) + lane;
+        to_fetch = mine * kParts;
+        fetch_part = 0;
+        fill = 0, fetch();
+        fill = kSlot, fetch();
+        slot = 0;
+    }
+
+    template <bool kExact>
+    __device__ __forceinline__ void run(const Op &op, const typename Op::Scratch &scratch, T *y, uint8_t *state,
+                                        uint32_t strip) {
+        if (mine == 0) return;
+        uint4 *yl = pinned(reinterpret_cast<uint4 *>(y) + me * (kParts * kHalf) + lane);
+        uint4 *out = pinned(reinterpret_cast<uint4 *>(state) + me * (kParts * kHalfChunks) + lane);
+        const uint32_t put_at = pinned(S::put_address(strip, lane));
+        const int64_t y_step = nwarps * (kParts * kHalf), out_step = nwarps * (kParts * kHalfChunks);
+        ahead = pinned(ahead);
+        for (int u = 0; u < mine; ++u, yl += y_step, out += out_step) {
+#pragma unroll
+            for (int part = 0; part < kParts; ++part) {
+                typename Subtile<T>::Raw raw[H];
+                copy_async_wait<1>();
+                raw[0].a = lds128<0>(ring_at + slot), raw[1].a = lds128<512>(ring_at + slot);
+                // the slot read one half ago is the one to fill now (two ahead of this one, modulo 3)
+                fill = slot == 0 ? 2 * kSlot : slot - kSlot;
+                slot = next_slot(slot);
+                fetch();
+                if (part == 0)
+                    forward_half<Op, T, S, kExact, 0, 0, H>(op, scratch, raw, yl, put_at, lane);
+                else
+                    forward_half<Op, T, S, kExact, H, H, H>(op, scratch, raw, yl, put_at, lane);
+            }
+            S::flush(strip, out, lane);
+        }
+        copy_async_wait<0>();
+    }
+};
 
 template <class Op, typename T, int U, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) forward_tiles_kernel(const T *x, T *y, uint8_t *state,
@@ -607,15 +631,17 @@ __global__ void __launch_bounds__(kThreads, MINB) forward_tiles_kernel(const T *
     __shared__ alignas(16) uint8_t strips[kWarps][(kStrip + 15) / 16 * 16];
     __shared__ alignas(16) uint8_t rings[kRing ? kWarps : 1][kRing ? 3 * 1024 : 16];   // cp.async input ring
     __shared__ typename Op::Scratch scratch;
-    op.prepare(scratch);
     const uint32_t strip = (uint32_t)__cvta_generic_to_shared(strips[threadIdx.x >> 5]);
     if constexpr (kRing) {
-        const uint32_t ring = (uint32_t)__cvta_generic_to_shared(rings[threadIdx.x >> 5]);
+        ForwardStream<Op, T> stream;
+        stream.start(x, ntiles * 2, (uint32_t)__cvta_generic_to_shared(rings[threadIdx.x >> 5]));
+        op.prepare(scratch);       // table set-up overlaps the first loads
         if (op.exact())
-            forward_stream<Op, T, true>(op, scratch, x, y, state, ntiles * 2, strip, ring);
+            stream.template run<true>(op, scratch, y, state, strip);
         else
-            forward_stream<Op, T, false>(op, scratch, x, y, state, ntiles * 2, strip, ring);
+            stream.template run<false>(op, scratch, y, state, strip);
     } else {
+        op.prepare(scratch);
         if (op.exact())
             forward_loop<Op, T, U, true>(op, scratch, x, y, state, ntiles, strip);
         else

@@ -126,6 +126,74 @@ Tensor softplus(Tensor &self, const Tensor &bounds, const Tensor &levels, double
     return StepwiseFunction::apply(self, bounds, levels, (int64_t)FEWBIT_SOFTPLUS, beta, threshold);
 }
 
+// --------------------------------------------------------- custom table: `stepwise` ----
+// Declared by the reference (fewbit/fewbit.cc:37) and wrapped by its `Stepwise` module
+// (fewbit/modules/activations.py:97-134), but without any kernel there.  Here: the activation
+// whose derivative the table describes -- continuous, piecewise linear, slopes `levels`, kinks at
+// `bounds`, zero at the anchor -- in place, saving only the packed codes and the levels.
+//
+// `parity` / `shift` (README.md:111-112 of the reference: "the parity property allows ... to
+// increase precision"): the table then describes only x > x0 and is mirrored about the point
+// (x0, s0) = shift (default (0, 0)) -- even: s(x0 - t) = s(x0 + t); odd: s(x0 - t) = 2 s0 -
+// s(x0 + t) -- which doubles the number of steps a table of a given size stands for.  The schema
+// types `shift` as integers; the Python module expands non-integer shifts itself.
+class CustomStepwiseFunction : public torch::autograd::Function<CustomStepwiseFunction> {
+public:
+    static Tensor forward(AutogradContext *ctx, const Tensor &self, const Tensor &bounds,
+                          const Tensor &levels, double anchor) {
+        check_activation(self, "stepwise");
+        TORCH_CHECK(levels.numel() >= 1 && levels.numel() <= 256,
+                    "fewbit: maximal number of steps is limited to 256, got ", levels.numel());
+        TORCH_CHECK(bounds.numel() + 1 == levels.numel(),
+                    "fewbit: size of `bounds` should be lesser than size of `levels` by one, got ",
+                    bounds.numel(), " and ", levels.numel());
+        c10::cuda::CUDAGuard guard(self.device());
+        auto stream = at::cuda::getCurrentCUDAStream();
+        const int bits = fewbit_bits_for_levels((int)levels.numel());
+        Tensor table = prepare_table(bounds, self, "bounds");
+        Tensor values = prepare_table(levels, self, "levels");
+        Tensor state = new_state(self, self.numel(), bits);
+        ctx->mark_dirty({self});
+        ctx->save_for_backward({state, values});
+        ctx->saved_data["bits"] = (int64_t)bits;
+        check_status(fewbit_stepwise_custom_forward(dtype_code(self, "activation"), self.data_ptr(),
+                                                    self.data_ptr(), state.data_ptr<uint8_t>(),
+                                                    self.numel(), bits, table.data_ptr(),
+                                                    (int)table.numel(), values.data_ptr(),
+                                                    (int)values.numel(), anchor, stream.stream()),
+                     "stepwise");
+        return self;
+    }
+
+    static variable_list backward(AutogradContext *ctx, variable_list grad_output) {
+        variable_list grads = StepwiseFunction::backward(ctx, std::move(grad_output));
+        return {grads[0], Tensor(), Tensor(), Tensor()};
+    }
+};
+
+// Not in the reference: the same operator with a real-valued anchor (the Python layer expands
+// mirrored tables itself, with non-integer shifts, and calls this).
+Tensor stepwise_anchored(Tensor &self, const Tensor &bounds, const Tensor &levels, double anchor) {
+    return CustomStepwiseFunction::apply(self, bounds, levels, anchor);
+}
+
+Tensor stepwise(Tensor &self, const Tensor &bounds, const Tensor &levels, std::optional<bool> parity,
+                at::OptionalIntArrayRef shift) {
+    const double x0 = shift.has_value() ? (double)(*shift)[0] : 0.0;
+    const double s0 = shift.has_value() ? (double)(*shift)[1] : 0.0;
+    if (!parity.has_value()) return CustomStepwiseFunction::apply(self, bounds, levels, x0);
+    TORCH_CHECK(bounds.dim() == 1 && levels.dim() == 1 && bounds.numel() + 1 == levels.numel(),
+                "fewbit::stepwise: `bounds` (one-dimensional) must be one shorter than `levels`");
+    TORCH_CHECK(2 * levels.numel() <= 256,
+                "fewbit::stepwise: a mirrored table doubles its steps; at most 128 levels, got ", levels.numel());
+    // even: the mirror image keeps its level; odd: it is reflected through s0
+    Tensor mirrored = *parity ? levels.flip(0) : (2.0 * s0 - levels.flip(0));
+    Tensor centre = torch::full({1}, x0, bounds.options());
+    Tensor full_bounds = torch::cat({2.0 * x0 - bounds.flip(0), centre, bounds});
+    Tensor full_levels = torch::cat({mirrored, levels});
+    return CustomStepwiseFunction::apply(self, full_bounds, full_levels, x0);
+}
+
 // ------------------------------------------------------------------- 1-bit family ----
 
 class PiecewiseFunction : public torch::autograd::Function<PiecewiseFunction> {
@@ -374,9 +442,10 @@ TORCH_LIBRARY(fewbit, m) {
     // Not in the reference: the projection of RandomizedLinear as one operator.
     m.def("sketch(Tensor x, int rows, int seed, int offset, int kind, float scale) -> Tensor");
     m.def("sketch_matrix(Tensor like, int rows, int cols, int seed, int offset, int kind) -> Tensor");
+    m.def("stepwise_anchored(Tensor(a!) self, Tensor bounds, Tensor levels, float anchor = 0.0) -> Tensor(a!)");
 
-    // Declared by the reference without any kernel (fewbit/fewbit.cc:37); kept so that the
-    // schema set is identical.  Calling it raises NotImplementedError, as in the reference.
+    // Declared by the reference without any kernel (fewbit/fewbit.cc:37); the schema is kept
+    // verbatim, the kernel is this package's (CustomStepwiseFunction above).
     m.def("stepwise   (Tensor(a!) self, Tensor bounds, Tensor levels, bool? parity=None, int[2]? shift=None) -> Tensor(a!)");
 }
 
@@ -404,6 +473,8 @@ TORCH_LIBRARY_IMPL(fewbit, AutogradCUDA, m) {
     m.impl("softsign", softsign);
     m.impl("tanh", tanh_);
     m.impl("tanhshrink", tanhshrink);
+    m.impl("stepwise", stepwise);
+    m.impl("stepwise_anchored", stepwise_anchored);
 }
 
 // As the reference: only gelu and the quantize pair exist for CPU tensors (fewbit/cpu/gelu.cc:74-76).

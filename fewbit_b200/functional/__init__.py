@@ -7,6 +7,6 @@ from .activations import (  # noqa: F401
     celu, elu, gelu, hardswish, logsigmoid, mish, selu, sigmoid, silu, softplus, softsign, tanh,
     tanhshrink)
 from .activations import (  # noqa: F401
-    CONTINOUS, CONTINUOUS, STEPWISE, StepwiseStore, make_table, store)
+    CONTINOUS, CONTINUOUS, STEPWISE, StepwiseStore, expand_table, make_table, store)
 # Linear layer with randomized (sketched) weight gradient.
 from .linear import linear_crs, linear_grp, linear_randomized  # noqa: F401

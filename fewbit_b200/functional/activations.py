@@ -30,7 +30,7 @@ CONTINOUS = ('celu', 'elu', 'gelu', 'hardswish', 'logsigmoid', 'mish', 'selu', '
              'softplus', 'softsign', 'tanh', 'tanhshrink')
 CONTINUOUS = CONTINOUS
 
-__all__ = STEPWISE + CONTINOUS + ('store', 'make_table')
+__all__ = STEPWISE + CONTINOUS + ('store', 'make_table', 'expand_table')
 
 BITS_DEFAULT = 3  # reference functional/activations.py:202
 
@@ -237,11 +237,82 @@ def _make_piecewise(name: str):
     return forward_call
 
 
-def stepwise(input: T.Tensor, borders: T.Tensor, levels: T.Tensor, parity=None, shift=None):
-    """Custom-table operator: declared by the reference (fewbit/fewbit.cc:37) but never
-    implemented there; kept for surface compatibility."""
-    raise NotImplementedError('fewbit.stepwise has no kernel in the reference either '
-                              '(functional/activations.py:132-142).')
+def expand_table(borders: T.Tensor, levels: T.Tensor, parity: Optional[bool] = None,
+                 shift: Optional[Tuple[float, float]] = None):
+    """The full table of a custom stepwise function and the point it is anchored at.
+
+    ``levels`` are the constant pieces of the derivative, ``borders`` the points between them
+    (with or without the two outer ends, as in the reference's ``Stepwise`` module).  With
+    ``parity`` the table describes only ``x > x0`` and is mirrored about ``(x0, s0) = shift``
+    (default ``(0, 0)``): ``True`` -- even, ``s(x0 - t) = s(x0 + t)``; ``False`` -- odd,
+    ``s(x0 - t) = 2 s0 - s(x0 + t)`` (GELU's derivative is odd about ``(0, 1/2)``).  Half a
+    table thus stands for twice the steps (reference README.md:111-112)."""
+    if borders.ndim != 1 or levels.ndim != 1:
+        raise ValueError('Expected number of dimensions of `borders` and `levels` is one.')
+    if borders.numel() > levels.numel():
+        borders = borders[1:-1]
+    if borders.numel() + 1 != levels.numel():
+        raise ValueError('Size of `borders` should be lesser than size of `levels` by one.')
+    x0, s0 = (float(shift[0]), float(shift[1])) if shift is not None else (0.0, 0.0)
+    if parity is not None:
+        if borders.numel() and float(borders.min()) <= x0:
+            raise ValueError('With `parity` the table describes x > shift[0]: all borders must lie above it.')
+        mirrored = levels.flip(0) if parity else 2.0 * s0 - levels.flip(0)
+        centre = T.full((1, ), x0, dtype=borders.dtype, device=borders.device)
+        borders = T.cat([2.0 * x0 - borders.flip(0), centre, borders])
+        levels = T.cat([mirrored, levels])
+    if levels.numel() > 256:
+        raise ValueError('Maximal number of step limited to 256.')
+    return borders, levels, x0
+
+
+def _piecewise_linear(x: T.Tensor, borders: T.Tensor, levels: T.Tensor, anchor: float):
+    """F(x) with F' = levels[code(x)], F continuous, F(anchor) = 0; and code(x)."""
+    b, l = borders.double(), levels.double()
+    rise = T.zeros(l.numel(), dtype=T.float64, device=b.device)      # rise[k] = F~(borders[k]), F~(borders[0]) = 0
+    if b.numel() > 1:
+        rise[1:b.numel()] = T.cumsum(l[1:b.numel()] * (b[1:] - b[:-1]), 0)
+    left = T.clamp(T.arange(l.numel(), device=b.device) - 1, 0, max(b.numel() - 1, 0))
+    if b.numel():
+        intercept = rise[left] - l * b[left]
+    else:
+        intercept = T.zeros_like(l)
+    anchor_t = T.tensor([anchor], dtype=b.dtype, device=b.device)
+    piece = int(T.searchsorted(b, anchor_t, right=False))
+    intercept = intercept - (l[piece] * anchor + intercept[piece])
+    code = T.searchsorted(borders.contiguous(), x.detach(), right=False)
+    value = T.addcmul(intercept.float()[code], levels.float()[code], x.float()).to(x.dtype)
+    return value, code
+
+
+class _StepwiseHostFunc(T.autograd.Function):
+    """CPU tensors: the same activation in PyTorch ops (out of place)."""
+
+    @staticmethod
+    def forward(ctx, input, borders, levels, anchor):
+        value, code = _piecewise_linear(input, borders.to(input), levels.to(input), anchor)
+        ctx.save_for_backward(code.to(T.uint8), levels.to(input))
+        return value
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        code, levels = ctx.saved_tensors
+        return levels[code.long()] * grad_output, None, None, None
+
+
+def stepwise(input: T.Tensor, borders: T.Tensor, levels: T.Tensor, parity: Optional[bool] = None,
+             shift: Optional[Tuple[float, float]] = None) -> T.Tensor:
+    """Custom-table activation (reference ``fewbit.functional.stepwise`` / operator
+    ``fewbit::stepwise``, fewbit/fewbit.cc:37 -- declared there, never implemented).
+
+    The table is the function: the result is the continuous piecewise-linear ``F`` whose slopes
+    are ``levels`` between ``borders``, with ``F(shift[0]) = 0``; backward multiplies the
+    incoming gradient by ``levels[code(x)]`` -- exactly ``F'``.  In place on CUDA tensors, where
+    only the bit-packed codes are saved; see :func:`expand_table` for ``parity`` / ``shift``."""
+    full_borders, full_levels, anchor = expand_table(borders, levels, parity, shift)
+    if input.device.type == 'cuda':
+        return _native_op('stepwise_anchored')(input, full_borders.to(input), full_levels.to(input), anchor)
+    return _StepwiseHostFunc.apply(input, full_borders, full_levels, anchor)
 
 
 for _name in CONTINOUS:

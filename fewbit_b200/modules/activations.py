@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import torch as T
 
 from .. import functional
-from ..functional.activations import SIGNATURES, stepwise
+from ..functional.activations import SIGNATURES, expand_table, stepwise
 
 # class name -> functional name
 STEPWISE = {'Hardshrink': 'hardshrink', 'Hardsigmoid': 'hardsigmoid', 'Hardtanh': 'hardtanh',
@@ -28,30 +28,43 @@ __all__ = tuple(STEPWISE) + ('Stepwise', ) + tuple(CONTINOUS)
 
 
 class Stepwise(T.nn.Module):
-    """User-supplied stepwise approximation (reference modules/activations.py:97-134).
+    """A custom stepwise activation (reference ``fewbit/modules/activations.py:97-134``): the
+    tensors ``borders`` and ``levels`` define the derivative's constant pieces, the module computes
+    the activation they integrate to and keeps only few-bit codes for backward
+    (:func:`fewbit_b200.functional.stepwise`).
 
-    :param borders: borders of the intervals (with or without the two outer sentinels).
-    :param levels: values of the constant pieces (at most 256).
+    :param borders: points between the pieces (with or without the two outer sentinels).
+    :param levels: values of the constant pieces (at most 256, mirrored pieces included).
+    :param parity: ``True`` / ``False``: the table covers ``x > shift[0]`` only and is mirrored
+                   evenly / oddly about ``shift`` (see :func:`functional.expand_table`).
+    :param shift: the point ``(x0, s0)`` the table is mirrored about and anchored at.
     """
 
     def __init__(self, borders: T.Tensor, levels: T.Tensor, parity: Optional[bool] = None,
                  shift: Optional[Tuple[float, float]] = None):
-        if borders.ndim != 1 or levels.ndim != 1:
-            raise ValueError('Exepected number of dimensions of `borders` and `levels` is one.')
+        full_borders, full_levels, anchor = expand_table(borders, levels, parity, shift)   # validates
         if borders.numel() > levels.numel():
             borders = borders[1:-1]
-        if borders.numel() + 1 != levels.numel():
-            raise ValueError('Size of `borders` should be lesser than size of `levels` by one.')
-        if levels.numel() > 256:
-            raise ValueError('Maximal number of step limited to 256.')
         super().__init__()
         self.register_buffer('borders', borders, True)
         self.register_buffer('levels', levels, True)
+        # the mirrored table is derived data: rebuilt from the two buffers above when they are loaded
+        self.register_buffer('_full_borders', full_borders, False)
+        self.register_buffer('_full_levels', full_levels, False)
         self.parity = parity
         self.shift = shift
+        self._anchor = anchor
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._full_borders, self._full_levels, self._anchor = expand_table(self.borders, self.levels, self.parity,
+                                                                           self.shift)
 
     def forward(self, xs: T.Tensor) -> T.Tensor:
-        return stepwise(xs, self.borders, self.levels, self.parity, self.shift)
+        return stepwise(xs, self._full_borders, self._full_levels, None, (self._anchor, 0.0))
+
+    def extra_repr(self) -> str:
+        return f'levels={self.levels.numel()}, parity={self.parity}, shift={self.shift}'
 
 
 class BuiltInStepwiseFunction(T.nn.Module):

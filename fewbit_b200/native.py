@@ -31,6 +31,7 @@ PROTOTYPES = {
     'fewbit_bits_for_levels': (_i, [_i]),
     'fewbit_stepwise_forward': (_i, [_i, _i, _vp, _vp, _vp, _i64, _i, _vp, _i, _d, _d, _vp]),
     'fewbit_stepwise_backward': (_i, [_i, _vp, _vp, _vp, _i64, _i, _vp, _i, _vp]),
+    'fewbit_stepwise_custom_forward': (_i, [_i, _vp, _vp, _vp, _i64, _i, _vp, _i, _vp, _i, _d, _vp]),
     'fewbit_piecewise_forward': (_i, [_i, _i, _vp, _vp, _vp, _i64, _d, _d, _vp]),
     'fewbit_piecewise_backward': (_i, [_i, _i, _vp, _vp, _vp, _i64, _d, _vp]),
     'fewbit_deflate': (_i, [_vp, _vp, _i64, _i, _vp]),
@@ -107,6 +108,14 @@ def stepwise_forward(func, x, y, state, bits, bounds, p0=1.0, p1=20.0, stream=No
                                         y.data_ptr(), state.data_ptr(), x.numel(), bits,
                                         bounds.data_ptr(), bounds.numel(), p0, p1, _stream(stream)),
           'fewbit_stepwise_forward')
+
+
+def stepwise_custom_forward(x, y, state, bits, bounds, levels, anchor=0.0, stream=None):
+    """y = F(x), F piecewise linear with slopes `levels` and kinks at `bounds`, F(anchor) = 0."""
+    check(lib().fewbit_stepwise_custom_forward(dtype_code(x), x.data_ptr(), y.data_ptr(), state.data_ptr(),
+                                               x.numel(), bits, bounds.data_ptr(), bounds.numel(),
+                                               levels.data_ptr(), levels.numel(), anchor, _stream(stream)),
+          'fewbit_stepwise_custom_forward')
 
 
 def stepwise_backward(state, gout, gin, bits, levels, stream=None):

@@ -92,6 +92,16 @@ FEWBIT_API int fewbit_stepwise_forward(int func, int dtype, const void *x, void 
 FEWBIT_API int fewbit_stepwise_backward(int dtype, const uint8_t *state, const void *gout, void *gin,
                              int64_t n, int bits, const void *levels, int nlevels, void *stream);
 
+/* Custom-table activation (reference schema `stepwise`, fewbit/fewbit.cc:37, and module
+ * `Stepwise`, fewbit/modules/activations.py:97-134; the reference declares the operator and ships
+ * no kernel for it).  The table is the function: `levels` (nlevels = nbounds + 1 values in the
+ * activation dtype) are the slopes of a continuous piecewise-linear F with kinks at `bounds`,
+ * F(anchor) = 0; y = F(x) (y may be x), state = pack(bucketize(x, bounds), bits) exactly as
+ * fewbit_stepwise_forward.  Its backward is fewbit_stepwise_backward with the same `levels`. */
+FEWBIT_API int fewbit_stepwise_custom_forward(int dtype, const void *x, void *y, uint8_t *state, int64_t n,
+                                   int bits, const void *bounds, int nbounds, const void *levels,
+                                   int nlevels, double anchor, void *stream);
+
 /* 1-bit family forward: y = f(x), state = pack(mask, 1).  Replaces Hardshrink..Threshold and
  * LeakyRelu (fewbit/cuda/codec.h:59-68).
  *   p0, p1 : lambd | min_val,max_val | negative_slope | threshold,value */
@@ -114,6 +124,13 @@ FEWBIT_API int fewbit_inflate(const uint8_t *state, int32_t *codes, int64_t n, i
  * streams so that H2D, kernel and D2H overlap, and returns after the last byte is back.
  * `state` stays a DEVICE pointer (it is the tensor saved for backward).  Tables are device
  * pointers as above.  `chunk_elems` <= 0 picks a default.
+ *
+ * Ordering: the staging streams are private to the library and not ordered against any stream of
+ * the caller.  Whatever produced `state` / the tables must have completed on the device before the
+ * call (e.g. cudaStreamSynchronize on the producing stream), and the call returns only after all
+ * of its own device work has completed -- on success AND on failure -- so the host buffers and
+ * `state` may be reused immediately.  One staging pipeline exists per device; concurrent calls for
+ * the same device are serialised, calls for different devices run side by side.
  */
 FEWBIT_API int fewbit_stepwise_forward_host(int func, int dtype, const void *x_host, void *y_host,
                                  uint8_t *state, int64_t n, int bits, const void *bounds,

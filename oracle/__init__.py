@@ -170,6 +170,31 @@ def stepwise_backward(state, gout, levels, bits: int | None = None) -> np.ndarra
     return gin
 
 
+def stepwise_custom_forward(x, bounds, levels, anchor: float = 0.0, bits: int | None = None):
+    """-> (y, state) of the custom-table operator `stepwise` (reference schema fewbit/fewbit.cc:37;
+    no reference kernel exists -- this restates the definition in include/fewbit_b200.h):
+    F continuous and piecewise linear, F' = levels[code(x)] with the reference's bucket search
+    (fewbit/cuda/codec.cu:118-131), F(anchor) = 0; y = fma(levels[code], x, intercept[code]).
+    fp32 arrays, or uint16 arrays holding bf16 bit patterns."""
+    x = np.ascontiguousarray(x).ravel()
+    bf16 = x.dtype == np.uint16
+    as_f32 = bf16_bits_to_f32 if bf16 else (lambda a: _c(a, np.float32))
+    b, l, xv = as_f32(bounds).astype(np.float64), as_f32(levels).astype(np.float64), as_f32(x)
+    if bits is None:
+        bits = bits_for_levels(l.size)
+    codes = bucketize(x, bounds)
+    rise = np.zeros(l.size)                       # rise[k] = F~(bounds[k]), F~(bounds[0]) = 0
+    if b.size > 1:
+        rise[1:b.size] = np.cumsum(l[1:b.size] * np.diff(b))
+    left = np.clip(np.arange(l.size) - 1, 0, max(b.size - 1, 0))
+    intercept = rise[left] - l * b[left] if b.size else np.zeros(l.size)
+    piece = int(np.searchsorted(b, np.float32(anchor), side='left'))
+    intercept = (intercept - (l[piece] * np.float64(np.float32(anchor)) + intercept[piece])).astype(np.float32)
+    # one fused multiply-add in fp32: the product of two floats is exact in double
+    y = (l[codes] * xv.astype(np.float64) + intercept[codes].astype(np.float64)).astype(np.float32)
+    return (f32_to_bf16_bits(y) if bf16 else y), deflate(codes, bits)
+
+
 # ------------------------------------------------------- piecewise, 1 bit --
 
 def piecewise_forward(func: str, x, p0: float = 0.0, p1: float = 0.0):

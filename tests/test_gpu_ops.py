@@ -8,10 +8,19 @@ import torch.nn.functional as F
 import fewbit_b200 as fewbit
 import oracle
 from fewbit_b200 import functional as FF
+from fewbit_b200 import native
 from fewbit_b200.functional import CONTINOUS, store
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
+
+
+def to_np(t: torch.Tensor) -> np.ndarray:
+    """fp32 -> float32 array, bf16 -> uint16 bit patterns (what the oracle takes)."""
+    t = t.detach().cpu().contiguous()
+    if t.dtype == torch.bfloat16:
+        return t.view(torch.int16).numpy().view(np.uint16)
+    return t.numpy()
 
 
 def _loaded_native():
@@ -140,7 +149,7 @@ def test_fp32_own_expm1_and_log1p_against_float64(name, bound):
     assert apart <= (5.0 if name == 'mish' else 3.0), f'{name}: {apart:.2f} ulp from ATen'
 
 
-@pytest.mark.parametrize('name', ['gelu', 'selu', 'softsign', 'hardswish'])
+@pytest.mark.parametrize('name', CONTINOUS)
 @pytest.mark.parametrize('bits', [5, 6, 7, 8])
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_shipped_5_to_8_bit_tables_through_the_kernels(name, bits, dtype):
@@ -149,9 +158,10 @@ def test_shipped_5_to_8_bit_tables_through_the_kernels(name, bits, dtype):
     whose borders crowd the bucket LUT (exact-search fallback) and the tables with a border on a
     jump of the derivative (selu at 0, hardswish at +-3)."""
     torch.manual_seed(bits)
-    x = (torch.randn(100003, device=DEV) * 3).to(dtype)
+    n = 300007                          # > one tile per warp of the grid for a few warps, plus a ragged tail
+    x = (torch.randn(n, device=DEV) * 3).to(dtype)
     x[:5] = torch.tensor([0.0, -0.0, 3.0, -3.0, 100.0], device=DEV).to(dtype)
-    g = torch.randn(100003, device=DEV).to(dtype)
+    g = torch.randn(n, device=DEV).to(dtype)
     leaf = x.clone().requires_grad_()
     getattr(FF, name)(leaf * 1, bits=bits).backward(g)      # the CUDA operators work in place
     borders, levels = store.get(name, bits, DEV, dtype)
@@ -227,8 +237,6 @@ def test_errors_are_loud():
         torch.ops.fewbit.gelu(x.clone(), torch.zeros(256, device=DEV), torch.zeros(257, device=DEV))
     with pytest.raises(RuntimeError):                           # in-place on a leaf that needs grad
         FF.gelu(torch.randn(8, device=DEV, requires_grad=True), bits=3)
-    with pytest.raises(NotImplementedError):
-        torch.ops.fewbit.stepwise(x.clone(), bounds, levels)
 
 
 def test_modules_and_piecewise_modules_on_cuda():
@@ -358,3 +366,58 @@ def test_second_device_is_respected():
     out = layer(x.requires_grad_())
     out.sum().backward()
     assert layer.weight.grad.device == torch.device(dev1) and torch.isfinite(layer.weight.grad).all()
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('bits', [1, 2, 3, 5, 8])
+def test_custom_stepwise_operator_against_the_oracle(dtype, bits):
+    """torch.ops.fewbit.stepwise (reference schema, fewbit/fewbit.cc:37; kernel: csrc/custom.cu):
+    packed codes bit-exact, values one fused multiply-add per element, gradient levels[code] * g
+    exact; ragged length, in place, through autograd."""
+    torch.manual_seed(bits)
+    nlevels = 1 << bits
+    bounds = torch.sort(torch.randn(nlevels - 1) * 1.5).values.to(dtype)
+    bounds = torch.unique_consecutive(bounds)
+    while bounds.numel() < nlevels - 1:                          # bf16 rounding may merge borders
+        bounds = torch.unique_consecutive(torch.sort(torch.cat([bounds, torch.randn(4).to(dtype) * 3])).values)[:nlevels - 1]
+    levels = torch.randn(nlevels).to(dtype)
+    n = 256 * 1024 + 77
+    x = (torch.randn(n, device=DEV) * 2).to(dtype)
+    g = torch.randn(n, device=DEV).to(dtype)
+    leaf = x.clone().requires_grad_()
+    y = torch.ops.fewbit.stepwise(leaf * 1.0, bounds.to(DEV), levels.to(DEV), None, [1, 0])
+    y.backward(g)
+    y_ref, state_ref = oracle.stepwise_custom_forward(to_np(x), to_np(bounds), to_np(levels), 1.0, bits)
+    gin_ref = oracle.stepwise_backward(state_ref, to_np(g), to_np(levels), bits)
+    state = native.new_state(x, bits)
+    out = torch.empty_like(x)
+    native.stepwise_custom_forward(x, out, state, bits, bounds.to(DEV), levels.to(DEV), 1.0)
+    torch.cuda.synchronize()
+    assert np.array_equal(state.cpu().numpy(), state_ref)
+    assert np.array_equal(to_np(leaf.grad), gin_ref)
+    assert torch.equal(out, y.detach())
+    if dtype == torch.float32:
+        err = np.abs(to_np(y.detach()).astype(np.float64) - y_ref.astype(np.float64))
+        assert np.all(err <= np.spacing(np.abs(y_ref)) + 1e-7 * np.abs(y_ref).max()), err.max()
+    else:
+        steps = np.abs(to_np(y.detach()).astype(np.int32) - y_ref.astype(np.int32))
+        assert (steps <= 1).all() and (steps == 0).mean() > 0.999
+
+
+def test_stepwise_module_mirrors_half_a_table_on_cuda():
+    """Stepwise(parity=...) (Python expansion, real-valued shift) and the operator's own integer
+    `shift` agree; a GELU table rebuilt from its upper half reproduces fewbit.GELU's gradient."""
+    borders, levels = store.get('gelu', 3, DEV, torch.float32)
+    inner = borders[1:-1]
+    x = torch.randn(1 << 16, device=DEV) * 2
+    upper = fewbit.Stepwise(inner[4:], levels[4:], parity=False, shift=(0.0, 0.5)).to(DEV)
+    a = x.clone().requires_grad_()
+    upper(a * 1.0).sum().backward()
+    codes = torch.searchsorted(upper._full_borders, x, right=False)
+    assert torch.equal(a.grad, upper._full_levels[codes])
+    even_py = fewbit.Stepwise(torch.tensor([1.0, 2.5]), torch.tensor([0.5, 0.25, 0.0]), parity=True, shift=(0.0, 0.0)).to(DEV)
+    even_op = torch.ops.fewbit.stepwise(x.clone(), torch.tensor([1.0, 2.5], device=DEV), torch.tensor([0.5, 0.25, 0.0], device=DEV),
+                                        True, [0, 0])
+    assert torch.equal(even_py(x.clone()), even_op)
+    y = even_py(x.clone())
+    assert torch.equal(y[x.abs() < 1.0], 0.5 * x[x.abs() < 1.0])

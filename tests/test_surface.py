@@ -86,13 +86,41 @@ def test_piecewise_on_cpu_tensors(name):
                                getattr(F, name)(x, *args))  # `bits` accepted and ignored (C-5)
 
 
-def test_stepwise_is_declared_but_not_implemented():
-    with pytest.raises(NotImplementedError):
-        FF.stepwise(torch.zeros(4), torch.zeros(1), torch.zeros(2))
+def test_custom_stepwise_tables():
+    """`stepwise` / `Stepwise`: the reference declares both (fewbit/fewbit.cc:37,
+    modules/activations.py:97-134) without a kernel; here the table is the function -- slopes
+    `levels` between `borders`, zero at the anchor -- and its gradient is levels[code] * g."""
     borders, levels = store.get('gelu', 3)
     m = fewbit.Stepwise(borders, levels)          # strips the +-100 sentinels
     assert m.borders.numel() == 7 and m.levels.numel() == 8
     assert set(m.state_dict()) == {'borders', 'levels'}
+    x = torch.linspace(-4, 4, 257, requires_grad=True)
+    y = m(x)
+    y.backward(torch.ones_like(y))
+    codes = torch.searchsorted(m.borders, x.detach(), right=False)
+    torch.testing.assert_close(x.grad, m.levels[codes], rtol=0, atol=0)
+    # the 3-bit table integrates to GELU up to the quantisation of its derivative
+    assert (y.detach() - F.gelu(x.detach())).abs().max().item() < 0.06 and abs(m(torch.zeros(1)).item()) == 0.0
+    # continuity across every kink, and slope = level inside every piece
+    eps = 1e-3
+    for k, b in enumerate(m.borders.tolist()):
+        lo, hi = m(torch.tensor([b - eps])), m(torch.tensor([b + eps]))
+        assert abs((hi - lo).item() - eps * (m.levels[k] + m.levels[k + 1]).item()) < 1e-5
+    # half a table, mirrored: GELU' is odd about (0, 1/2)
+    half = fewbit.Stepwise(m.borders[4:], m.levels[4:], parity=False, shift=(0.0, 0.5))
+    assert half._full_levels.numel() == 8 and half._full_borders.numel() == 7
+    torch.testing.assert_close(half._full_levels[:4], 1.0 - m.levels[4:].flip(0))
+    pts = torch.tensor([1.3, 2.0, 0.1])
+    torch.testing.assert_close(half(-pts), half(pts) - pts)                # F(-t) = F(t) - t
+    even = FF.expand_table(torch.tensor([2.0, 3.0]), torch.tensor([0.5, 0.25, 0.0]), True, (1.0, 0.0))
+    assert even[0].tolist() == [-1.0, 0.0, 1.0, 2.0, 3.0] and even[1].tolist() == [0.0, 0.25, 0.5, 0.5, 0.25, 0.0] and even[2] == 1.0
+    with pytest.raises(ValueError, match='above'):
+        FF.expand_table(torch.tensor([-1.0, 2.0]), torch.tensor([0.5, 0.25, 0.0]), True)
+    with pytest.raises(ValueError, match='256'):
+        FF.expand_table(torch.arange(1, 200.0), torch.zeros(200), False)
+    loaded = fewbit.Stepwise(torch.tensor([1.0]), torch.tensor([1.0, 2.0]), parity=True)
+    loaded.load_state_dict({'borders': torch.tensor([2.0]), 'levels': torch.tensor([1.0, 3.0])})
+    assert loaded._full_borders.tolist() == [-2.0, 0.0, 2.0] and loaded._full_levels.tolist() == [3.0, 1.0, 1.0, 3.0]
     with pytest.raises(ValueError):
         fewbit.Stepwise(torch.zeros(3), torch.zeros(8))
     with pytest.raises(ValueError):
