@@ -472,34 +472,43 @@ def side_measurements(dev, peak, traffic_table):
     flush = torch.ones(256 << 20, dtype=torch.float32, device=dev)     # 1 GiB: read before every timed launch
     sink = torch.zeros((), dtype=torch.float32, device=dev)
 
-    def timed(fn, reps=25, skip=5):
+    def timed(fn, reps=25, skip=5, group=3):
+        """Median over reps of (time of `group` launches, one per buffer set) / group.  Before every
+        group the L2 is flushed by reading 1 GiB; the launches of a group touch different buffers,
+        so every one of them finds its inputs in HBM.  (Events around a single ~40 us launch add
+        ~2 us of their own; a group amortises that.)"""
         ts = []
         for it in range(reps):
-            sink.copy_(flush.sum())                                    # read 1 GiB >> L2; ~170 us of GPU time, during
-                                                                       # which the timed launch is already enqueued
+            sink.copy_(flush.sum())
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b.record()
+            a.record()
+            for k in range(group):
+                fn(k)
+            b.record()
             torch.cuda.synchronize()
             if it >= skip:
-                ts.append(a.elapsed_time(b))
+                ts.append(a.elapsed_time(b) / group)
         return statistics.median(ts)
 
-    where = '128x128x3072 elements, median of 20 single launches, L2 flushed by reading 1 GiB before each'
+    where = ('128x128x3072 elements; median of 20 groups of 3 launches on 3 distinct buffer sets, L2 flushed by '
+             'reading 1 GiB before each group (inputs always come from HBM)')
     for tag, dtype, es in (('f32', torch.float32, 4), ('bf16', torch.bfloat16, 2)):
         borders, levels = store.get('gelu', 3, dev, dtype)
         bounds = borders[1:-1].contiguous()
-        x = (torch.randn(n, device=dev) * 2).to(dtype)
-        g = torch.randn(n, device=dev).to(dtype)
-        y, gin = torch.empty_like(x), torch.empty_like(g)
-        state = native.new_state(x, 3)
+        xs = [(torch.randn(n, device=dev) * 2).to(dtype) for _ in range(3)]
+        gs = [torch.randn(n, device=dev).to(dtype) for _ in range(3)]
+        ys, gins = [torch.empty_like(t) for t in xs], [torch.empty_like(t) for t in gs]
+        states = [native.new_state(xs[0], 3) for _ in range(3)]
         nbytes = n * (2 * es) + n * 3 // 8
-        for label, key, fn in (('fwd', f'gelu3_{tag}_forward', lambda: native.stepwise_forward('gelu', x, y, state, 3, bounds)),
-                               ('bwd', f'levels3_{tag}_backward', lambda: native.stepwise_backward(state, g, gin, 3, levels))):
+        for label, key, fn in (('fwd', f'gelu3_{tag}_forward',
+                                lambda k: native.stepwise_forward('gelu', xs[k], ys[k], states[k], 3, bounds)),
+                               ('bwd', f'levels3_{tag}_backward',
+                                lambda k: native.stepwise_backward(states[k], gs[k], gins[k], 3, levels))):
             ms = timed(fn)
             out[f'gelu3_{tag}_{label}_GBps'] = nbytes / (ms / 1e3) / 1e9
             rooflines.append(roofline_entry(f'gelu3_{tag}_{"forward" if label == "fwd" else "backward"}', nbytes, ms,
                                             peak, traffic_table.get(key), where))
-        del x, g, y, gin, state
+        del xs, gs, ys, gins, states
     out['note'] = where
     tokens, rows, features = 16384, 3276, 768
     x = torch.randn(tokens, features, device=dev).to(torch.bfloat16)
@@ -513,7 +522,7 @@ def side_measurements(dev, peak, traffic_table):
     for kind in ('gaussian', 'rademacher'):
         calls = [0]
 
-        def run():
+        def run(_):
             calls[0] += 1
             native.sketch_forward(x, rows, 1, 4 * calls[0], kind, 1.0 / rows, out=result, workspace=workspace)
 
@@ -522,8 +531,8 @@ def side_measurements(dev, peak, traffic_table):
         out[f'sketch_{kind}_D768_TFLOPs'] = flops / (ms / 1e3) / 1e12
         rooflines.append(roofline_entry(
             f'sketch_{kind}_D768', flops, ms, tensor_peak, traffic_table.get('sketch_kernel'),
-            'N=16384 P=3276 D=768 bf16, median of 20 calls of fewbit_sketch_forward with preallocated output and '
-            'workspace (projection kernel + split-K reduction), L2 flushed by reading before each',
+            'N=16384 P=3276 D=768 bf16, median of 20 groups of 3 calls of fewbit_sketch_forward with preallocated output '
+            'and workspace (projection kernel + split-K reduction), L2 flushed by reading 1 GiB before each group',
             bound='tensor', unit='TFLOP/s', scale=1e12, peak_source='MEASURED_PEAKS.json bf16_tflops (burst)'))
     out['sketch_peak_bf16_TFLOPs'] = tensor_peak
     del flush

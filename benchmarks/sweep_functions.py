@@ -11,7 +11,7 @@ data-path collective), and rank 0 prints the aggregate GB/s = sum over ranks and
 rank's fraction of peak.
 
 GB/s = algorithmic bytes n (s + s + b/8) / CUDA-event time (12 back-to-back launches over four
-rotating buffer sets so nothing is served from L2, median of 5 rounds).  Bits 1-4 use the
+rotating buffer sets so nothing is served from L2, replayed from a CUDA graph, median of 5 rounds).  Bits 1-4 use the
 built-in tables, 5-8 the shipped optimal tables (`--tables synthetic`: `make_table`).
 """
 from __future__ import annotations
@@ -52,16 +52,29 @@ def across_ranks(value):
 
 
 def timed(fn, reps=12, rounds=5):
+    """ms per launch: `reps` back-to-back launches captured in one CUDA graph (so that the host's
+    launch cost, which varies from box to box and approaches the ~40 us of a kernel, stays out of the
+    number), replayed `rounds` times between CUDA events; median."""
     for _ in range(3):
         fn()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        fn()
+        side.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(reps):
+                fn()
+    torch.cuda.synchronize()
     if WORLD > 1:
         torch.distributed.barrier()
     ts = []
+    graph.replay()
     for _ in range(rounds):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(reps):
-            fn()
+        graph.replay()
         b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b) / reps)

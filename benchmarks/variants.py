@@ -51,12 +51,21 @@ def child():
 
         for _ in range(3):
             fwd()
+        torch.cuda.synchronize()
+        side, graph = torch.cuda.Stream(), torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            fwd()
+            side.synchronize()
+            with torch.cuda.graph(graph, stream=side):      # host launch cost stays out of the number
+                for _ in range(12):
+                    fwd()
+        torch.cuda.synchronize()
+        graph.replay()
         ts = []
         for _ in range(5):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            for _ in range(12):
-                fwd()
+            graph.replay()
             b.record()
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(b) / 12)

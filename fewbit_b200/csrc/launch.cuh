@@ -86,7 +86,7 @@ template <class Op, typename T> struct TileConfig {
         static constexpr int kMinBlocks = FEWBIT_TILE_HINTS ? O::kMinBlocksF32 : FEWBIT_MINB_HEAVY_F32;
     };
     static constexpr int kSubtiles =
-        kHeavy ? (sizeof(T) == 4 ? Hint<Op>::kSubtiles : FEWBIT_U_HEAVY)
+        kHeavy ? (sizeof(T) == 4 && !wants_stream_f32<Op>::value ? Hint<Op>::kSubtiles : FEWBIT_U_HEAVY)
                : (sizeof(T) == 2 ? FEWBIT_U_LIGHT_BF16 : FEWBIT_U_LIGHT_F32);
     static constexpr int kMinBlocks =
         kHeavy ? (sizeof(T) == 2 ? FEWBIT_MINB_HEAVY_BF16 : Hint<Op>::kMinBlocks) : FEWBIT_MINB_LIGHT;
@@ -94,13 +94,13 @@ template <class Op, typename T> struct TileConfig {
 
 // Resident CTAs per SM for `kernel` (occupancy API, cached per instantiation), overridable
 // with FEWBIT_B200_CTAS_PER_SM for tuning runs.
-template <auto kernel> int resident_ctas(int most) {
+template <auto kernel> int resident_ctas(int most, int dynamic_smem = 0) {
     // the answer depends on the kernel and the architecture only (sm_100a everywhere): caching it
     // per instantiation, not per device, is enough; a racing first call computes the same value
     static std::atomic<int> cached{0};
     if (cached.load(std::memory_order_relaxed) == 0) {
         int blocks = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, kThreads, 0) !=
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, kThreads, dynamic_smem) !=
                 cudaSuccess ||
             blocks < 1)
             blocks = 1;
@@ -128,9 +128,22 @@ cudaError_t launch_forward(const T *x, T *y, uint8_t *state, int64_t n, const Op
     const int64_t ntiles = vector_aligned<T>(x, y, state) ? n / kTile : 0;
     if (ntiles > 0) {
         constexpr auto kernel = forward_tiles_kernel<Op, T, U, TileConfig<Op, T>::kMinBlocks>;
+        constexpr int kRing = ring_bytes<Op, T, U>();       // dynamic shared memory: the cp.async input ring
+        if constexpr (kRing > 0) {
+            // static + dynamic shared memory may pass the 48 KB default: opt in once per device
+            static std::atomic<unsigned long long> configured{0};
+            int device = 0;
+            cudaGetDevice(&device);
+            const unsigned long long bit = 1ull << (device & 63);
+            if (!(configured.load(std::memory_order_relaxed) & bit)) {
+                cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRing);
+                if (e != cudaSuccess) return e;
+                configured.fetch_or(bit, std::memory_order_relaxed);
+            }
+        }
         const int64_t want = (ntiles + kWarps - 1) / kWarps;
-        const int64_t cap = (int64_t)sm_count() * resident_ctas<kernel>(TileConfig<Op, T>::kMaxCtasPerSm);
-        kernel<<<(unsigned)std::min(want, cap), kThreads, 0, stream>>>(x, y, state, ntiles, op);
+        const int64_t cap = (int64_t)sm_count() * resident_ctas<kernel>(TileConfig<Op, T>::kMaxCtasPerSm, kRing);
+        kernel<<<(unsigned)std::min(want, cap), kThreads, kRing, stream>>>(x, y, state, ntiles, op);
         note_launch();
     }
     const int64_t first = ntiles * kTile;

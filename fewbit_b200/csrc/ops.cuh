@@ -37,6 +37,11 @@ struct NoScratch {
 // Tables shorter than 2^B - 1 are padded with +inf (never counted).
 // =====================================================================================
 
+#ifndef FEWBIT_FEW_CELLS
+#define FEWBIT_FEW_CELLS 0   // A/B switch: try a bank-conflict-free 32-cell table first (bf16, 3-4 bits).  Measured:
+                             // no effect (3-bit GELU bf16 86 % either way, profiles/r02_stream_modes.txt) -- with the
+                             // input ring those kernels are bound by instruction issue, not by the gather
+#endif
 template <typename T, int B, bool kInRegisters = (B <= 2)> struct Bucketizer;
 
 template <typename T, int B> struct Bucketizer<T, B, true> {
@@ -90,6 +95,8 @@ __device__ __forceinline__ unsigned long long pack2(float v) {
 // (Needs denormals: the build refuses -ftz=true / --use_fast_math, see the #error above.)
 struct CellMap {
     float scale, offset;
+    float last_cell;      // the number of cells - 1, as the denormal float whose bit pattern it is
+    __device__ __forceinline__ void set_cells(int cells) { last_cell = __uint_as_float((uint32_t)(cells - 1)); }
     template <typename T> __device__ __forceinline__ void fit(const T *bounds, int nbounds) {
         const float lo = nbounds > 0 ? to_float<T>(bounds[0]) : 0.0f;
         const float hi = nbounds > 0 ? to_float<T>(bounds[nbounds - 1]) : 0.0f;
@@ -103,18 +110,17 @@ struct CellMap {
         }
         if (!(fabsf(offset) < CUDART_INF_F)) offset = 0.5f;
     }
-    template <int kCells> __device__ __forceinline__ uint32_t cell(float x) const {
+    __device__ __forceinline__ uint32_t cell(float x) const {
         const float t = __saturatef(fmaf(x, scale, offset));
-        return __float_as_uint(__fmul_rn(t, __uint_as_float((uint32_t)(kCells - 1))));
+        return __float_as_uint(__fmul_rn(t, last_cell));
     }
     // two elements per multiply (mul.rn.f32x2): the clamp has no packed form, the product does
-    template <int kCells>
     __device__ __forceinline__ void cells(float x0, float x1, uint32_t &c0, uint32_t &c1) const {
         const float t0 = __saturatef(fmaf(x0, scale, offset));
         const float t1 = __saturatef(fmaf(x1, scale, offset));
         unsigned long long t2, a2;
         asm("mov.b64 %0, {%1, %2};" : "=l"(t2) : "f"(t0), "f"(t1));
-        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(a2) : "l"(t2), "l"(pack2(__uint_as_float((uint32_t)(kCells - 1)))));
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(a2) : "l"(t2), "l"(pack2(last_cell)));
         asm("mov.b64 {%0, %1}, %2;" : "=r"(c0), "=r"(c1) : "l"(a2));
     }
 };
@@ -137,23 +143,35 @@ template <int kSize> __device__ __noinline__ uint32_t search_exact(uint32_t sort
 // Borders -> cells, shared by both table layouts: fills s.bounds / s.bound_cell, then calls
 // `emit(cell, k, has_border)` for every cell with k = #{borders in earlier cells}; returns
 // (block-wide) whether some cell holds two or more borders.
-template <int kSize, int kCells, typename T, class Scratch, class Emit>
-__device__ __forceinline__ bool build_cells(const CellMap &map, const T *bounds, int nbounds, Scratch &s,
+template <int kSize, typename T, class Scratch, class Emit>
+__device__ __forceinline__ bool build_cells(const CellMap &map, int cells, const T *bounds, int nbounds, Scratch &s,
                                             Emit emit) {
+    __syncthreads();       // a second attempt (another cell count) overwrites what the first one read
     for (int i = threadIdx.x; i < kSize; i += blockDim.x) {
         const float v = i < nbounds ? to_float<T>(bounds[i]) : CUDART_INF_F;
         s.bounds[i] = v;
-        s.bound_cell[i] = i < nbounds ? (uint16_t)map.cell<kCells>(v) : (uint16_t)kCells;
+        s.bound_cell[i] = i < nbounds ? (uint16_t)map.cell(v) : (uint16_t)cells;
     }
     __syncthreads();
+    // Each warp fills one contiguous run of cells, lanes interleaved (coalesced writes).  The cells
+    // of a lane ascend, and so does k = #{borders in earlier cells}: one binary search for the
+    // first cell, then k only ever advances -- by the few borders that fall between two cells of
+    // the lane.  (A binary search per cell made the 4096-cell table of the 8-bit kernels cost
+    // ~5 us per CTA, a tenth of the kernel.)
     int shared_cell = 0;
-    for (int c = threadIdx.x; c < kCells; c += blockDim.x) {
+    const int per_warp = (cells + kWarps - 1) / kWarps;
+    const int first = (threadIdx.x >> 5) * per_warp, last = min(cells, first + per_warp);
+    int c = first + (threadIdx.x & 31);
+    if (c < last) {
         int k = 0;  // first border whose cell is >= c
 #pragma unroll
         for (int step = kSize >> 1; step >= 1; step >>= 1)
             if (s.bound_cell[k + step - 1] < c) k += step;
-        shared_cell |= (k + 1 < kSize && s.bound_cell[k + 1] == c) ? 1 : 0;
-        emit(c, k, k < kSize && s.bound_cell[k] == c);
+        for (; c < last; c += 32) {
+            while (k < kSize && s.bound_cell[k] < c) ++k;
+            shared_cell |= (k + 1 < kSize && s.bound_cell[k + 1] == c) ? 1 : 0;
+            emit(c, k, k < kSize && s.bound_cell[k] == c);
+        }
     }
     return __syncthreads_or(shared_cell) != 0;
 }
@@ -178,7 +196,8 @@ __device__ __forceinline__ bool build_cells(const CellMap &map, const T *bounds,
 template <typename T, int B> struct Bucketizer<T, B, false> {
     static constexpr bool kOneGather = sizeof(T) == 2;
     static constexpr int kSize = 1 << B;  // borders padded with +inf to a power of two
-    static constexpr int kCells = kOneGather ? (16 << B) : B == 3 ? 128 : B == 4 ? 256 : B == 5 ? 512 : 2048;
+    static constexpr int kCells = kOneGather ? (B == 6 ? 2048 : 16 << B)      // 128 256 512 2048 2048 4096
+                                            : B == 3 ? 128 : B == 4 ? 256 : B == 5 ? 512 : B == 8 ? 4096 : 2048;
     static constexpr int kShift = B <= 6 ? 2 : 0;   // byte entries hold k << kShift
     static constexpr int kCopies = B <= 4 ? 4 : 2;
     struct Scratch {
@@ -202,19 +221,30 @@ template <typename T, int B> struct Bucketizer<T, B, false> {
         if ((bits >> 31) && low != 0) return (bits - 0x10000u) | low;
         return bits | low;                          // (+inf: a NaN pattern unless k == 0)
     }
+    // bf16 at 3 and 4 bits: a table of 32 words has one word per bank -- the gather is free of
+    // bank conflicts (with 128 words ncu counted 2.6 wavefronts per gather, and the shared-memory
+    // pipe is what bounds these kernels).  Most shipped 3-bit tables separate at 32 cells; if a
+    // table does not, the full-size table is built instead.
+    static constexpr int kFewCells = (FEWBIT_FEW_CELLS && kOneGather && B <= 4) ? 32 : kCells;
     __device__ __forceinline__ void prepare(Scratch &s) {
         map.fit(bounds, nbounds);
-        crowded = build_cells<kSize, kCells>(map, bounds, nbounds, s, [&](int c, int k, bool has) {
+        auto emit = [&](int c, int k, bool has) {
             if constexpr (kOneGather)
                 s.word[c] = encode(has ? s.bounds[k] : CUDART_INF_F, (uint32_t)k);
             else
                 s.lut[c] = (uint8_t)(k << kShift);
-        });
+        };
+        map.set_cells(kFewCells);
+        crowded = build_cells<kSize>(map, kFewCells, bounds, nbounds, s, emit);
+        if (kFewCells != kCells && crowded) {
+            map.set_cells(kCells);
+            crowded = build_cells<kSize>(map, kCells, bounds, nbounds, s, emit);
+        }
     }
     __device__ __forceinline__ uint32_t half(const Scratch &s, float x0, float x1, float x2, float x3) const {
         uint32_t c0, c1, c2, c3;
-        map.cells<kCells>(x0, x1, c0, c1);
-        map.cells<kCells>(x2, x3, c2, c3);
+        map.cells(x0, x1, c0, c1);
+        map.cells(x2, x3, c2, c3);
         uint32_t acc;
         float b0, b1, b2, b3;
         if constexpr (kOneGather) {
@@ -709,29 +739,35 @@ template <class Fn> struct has_pairs32<Fn, std::enable_if_t<Fn::kPaired32>> : st
 // register budget is set for).  Measured on B200 over {1,4}, {2,4}, {2,3}, {4,3} for every function
 // (3-bit, 128x128x3072; profiles/r01_function_sweep_3bit.md): short formulas want few loads in flight
 // per warp and four CTAs, libdevice-heavy ones the registers of three CTAs.
+#ifndef FEWBIT_STREAM_F32
+#define FEWBIT_STREAM_F32 1   // 0: no fp32 kernel streams its input; 1: those marked below; 2: all
+#endif
 template <class Fn> struct TileHintF32 {
     static constexpr int kSubtiles = 4, kMinBlocks = 3;               // gelu, logsigmoid
+    static constexpr bool kStream = FEWBIT_STREAM_F32 >= 1;
 };
-#define FEWBIT_TILE_HINT_F32(FN, U, MINB)                                 \
+#define FEWBIT_TILE_HINT_F32(FN, U, MINB, STREAM)                         \
     template <> struct TileHintF32<FN> {                                  \
         static constexpr int kSubtiles = U, kMinBlocks = MINB;            \
+        static constexpr bool kStream = FEWBIT_STREAM_F32 >= 2 || (FEWBIT_STREAM_F32 == 1 && STREAM); \
     };
-FEWBIT_TILE_HINT_F32(CeluFn, 1, 4)
-FEWBIT_TILE_HINT_F32(EluFn, 1, 4)
-FEWBIT_TILE_HINT_F32(SeluFn, 1, 4)
-FEWBIT_TILE_HINT_F32(HardswishFn, 1, 4)
-FEWBIT_TILE_HINT_F32(SoftsignFn, 2, 3)
-FEWBIT_TILE_HINT_F32(TanhFn, 2, 3)
-FEWBIT_TILE_HINT_F32(TanhshrinkFn, 2, 3)
-FEWBIT_TILE_HINT_F32(SigmoidFn, 2, 3)
-FEWBIT_TILE_HINT_F32(MishFn, 2, 3)
-FEWBIT_TILE_HINT_F32(SiluFn, 2, 3)
-FEWBIT_TILE_HINT_F32(SoftplusFn, 2, 4)
+FEWBIT_TILE_HINT_F32(CeluFn, 1, 4, 0)
+FEWBIT_TILE_HINT_F32(EluFn, 1, 4, 0)
+FEWBIT_TILE_HINT_F32(SeluFn, 1, 4, 0)
+FEWBIT_TILE_HINT_F32(HardswishFn, 1, 4, 0)
+FEWBIT_TILE_HINT_F32(SoftsignFn, 2, 3, 0)
+FEWBIT_TILE_HINT_F32(TanhFn, 2, 3, 0)
+FEWBIT_TILE_HINT_F32(TanhshrinkFn, 2, 3, 0)
+FEWBIT_TILE_HINT_F32(SigmoidFn, 2, 3, 0)
+FEWBIT_TILE_HINT_F32(MishFn, 2, 3, 0)
+FEWBIT_TILE_HINT_F32(SiluFn, 2, 3, 0)
+FEWBIT_TILE_HINT_F32(SoftplusFn, 2, 3, 1)
 #undef FEWBIT_TILE_HINT_F32
 
 template <class Fn, typename T, int B> struct QuantizeOp {
     static constexpr int kBits = B;
     static constexpr int kSubtilesF32 = TileHintF32<Fn>::kSubtiles, kMinBlocksF32 = TileHintF32<Fn>::kMinBlocks;
+    static constexpr bool kStreamF32 = TileHintF32<Fn>::kStream && B >= 3;   // 1-2 bits: measured slower (89 -> 81 %)
     static constexpr bool kHeavy = true;  // transcendental math: see TileConfig in launch.cuh
     using Scratch = typename Bucketizer<T, B>::Scratch;
     Fn fn;

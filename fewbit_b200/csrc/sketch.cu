@@ -72,7 +72,10 @@ int sm_count();
 
 namespace sketch {
 
-constexpr int kThreads = 512;
+#ifndef FEWBIT_SKETCH_THREADS
+#define FEWBIT_SKETCH_THREADS 512
+#endif
+constexpr int kThreads = FEWBIT_SKETCH_THREADS;     // warp 0: TMA, warp 1: MMA, the rest generate S
 constexpr int kStages = 3;
 constexpr int kBlockK = 64;            // tokens per stage
 constexpr int kFeaturesPerCta = 384;   // 3 MMA M-blocks of 128
@@ -82,7 +85,7 @@ constexpr int kXStageBytes = (kFeaturesPerCta / 64) * kBoxBytes;   // 49152
 constexpr int kSStageBytes = kMaxRows * 128;                  // 20480: BN rows x 64 bf16
 constexpr int kStageBytes = kXStageBytes + kSStageBytes;
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* alignment */ + 256 /* barriers */;
-constexpr int kGeneratorWarps = 14;
+constexpr int kGeneratorWarps = kThreads / 32 - 2;
 constexpr int kGeneratorThreads = kGeneratorWarps * 32;
 constexpr int kTmemColumns = 512;
 

@@ -34,10 +34,23 @@ constexpr int kSubtile = 256;  // elements per warp per round of 128-bit loads
 #define FEWBIT_LD_MODE 1  // 0: ld.global   1: ld.global.L1::no_allocate   2: ld.global.cs
 #endif
 #ifndef FEWBIT_PREFETCH
-// Input prefetch of the math-heavy bf16 forward kernels.  0: load a tile, compute it.
-// 1: software pipeline through registers.  2: cp.async ring in shared memory (the default).
+// Input prefetch of the math-heavy forward kernels.  0: load a tile, compute it.
+// 1: software pipeline through registers.  2: streamed half tiles (ForwardStream).
 #define FEWBIT_PREFETCH 2
 #endif
+#ifndef FEWBIT_STREAM_MODE
+// How a streamed kernel gets its input early.  0: cp.async ring in shared memory.  1: bulk
+// prefetch into L2 two halves ahead, plain loads at the point of use.  2 (default): per kernel --
+// the ring decouples the load latency completely and wins wherever instruction issue is the
+// limit (fp32, bf16 up to 4 bits: 3-bit GELU bf16 87 % against 80 %); from 5 bits on the bf16
+// kernels are bound by shared-memory wavefronts (ncu: that pipe 70-80 % busy, table gathers at
+// 3.3 wavefronts each), the ring's round trip through shared memory is a quarter of those, and
+// the L2 prefetch wins (7-bit hardswish 85 % against 82 %).  profiles/r02_stream_modes.txt.
+#define FEWBIT_STREAM_MODE 2
+#endif
+template <typename T, int B> constexpr int stream_mode() {
+    return FEWBIT_STREAM_MODE != 2 ? FEWBIT_STREAM_MODE : (sizeof(T) == 2 && B >= 5 ? 1 : 0);
+}
 #ifndef FEWBIT_ST_MODE
 #define FEWBIT_ST_MODE 1  // 0: st.global   1: st.global.L1::no_allocate   2: st.global.cs
 #endif
@@ -235,6 +248,11 @@ template <int kOffset> __device__ __forceinline__ void copy_async16(uint32_t dst
 __device__ __forceinline__ void copy_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int kPending> __device__ __forceinline__ void copy_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+}
+// Ask for `bytes` (a multiple of 16) at `src` (16-byte aligned) to be brought into L2; one lane
+// speaks for the warp.
+__device__ __forceinline__ void prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
 // Write the low B bytes of `octet` to the (B-byte aligned) shared-memory address a + kOffset.
@@ -521,8 +539,15 @@ __device__ __forceinline__ void forward_loop(const Op &op, const typename Op::Sc
 // Which forward kernels stream their input through the cp.async ring (forward_stream below).
 template <class Op, typename = void> struct wants_stream : std::true_type {};
 template <class Op> struct wants_stream<Op, std::enable_if_t<!Op::kStreamInput>> : std::false_type {};
+template <class Op, typename = void> struct wants_stream_f32 : std::false_type {};
+template <class Op> struct wants_stream_f32<Op, std::enable_if_t<Op::kStreamF32>> : std::true_type {};
 template <class Op, typename T, int U> constexpr bool streams_input() {
-    return Op::kHeavy && wants_stream<Op>::value && sizeof(T) == 2 && U == 4 && FEWBIT_PREFETCH == 2;
+    return Op::kHeavy && wants_stream<Op>::value && U == 4 && FEWBIT_PREFETCH == 2 &&
+           (sizeof(T) == 2 || wants_stream_f32<Op>::value);
+}
+// Bytes of the cp.async input ring of one CTA (dynamic shared memory; 0: kernel does not stream).
+template <class Op, typename T, int U> constexpr int ring_bytes() {
+    return streams_input<Op, T, U>() && stream_mode<T, Op::kBits>() == 0 ? kWarps * 3 * 2 * Subtile<T>::kVectors * 16 : 0;
 }
 
 // The math-heavy bf16 forward kernels: the same work, streamed.
@@ -548,13 +573,16 @@ template <class Op, typename T> struct ForwardStream {
     using S = Stager<T, B, kParts * H>;
     static constexpr int kHalf = H * Subtile<T>::kVectors;                // 128-bit vectors per half
     static constexpr int kHalfChunks = H * subtile_bytes<B>() / 16;       // 16-byte chunks of packed state per half
-    static constexpr uint32_t kSlot = H * 512;
+    static constexpr int kSub = Subtile<T>::kVectors * 16;                // bytes of one subtile: 512 (bf16), 1024 (fp32)
+    static constexpr uint32_t kSlot = H * kSub;
+    static constexpr int kMode = stream_mode<T, B>();
 
     int lane;
     int64_t nwarps, me;
     int mine;                 // units of this warp (0: nothing to do)
     uint32_t ring_at;         // this lane's 16 bytes of slot 0
     const uint4 *ahead;       // first vector of the next half to request: the fetch stream runs two halves ahead
+    const uint4 *now;         // first vector of the half to compute next (L2-prefetch mode)
     int to_fetch;
     uint32_t fill, slot;      // byte offsets of the slot to fill next / to read next
     int fetch_part;
@@ -563,7 +591,13 @@ template <class Op, typename T> struct ForwardStream {
 
     __device__ __forceinline__ void fetch() {
         if (to_fetch > 0) {
-            copy_async16<0>(ring_at + fill, ahead), copy_async16<512>(ring_at + fill, ahead + Subtile<T>::kVectors);
+            if constexpr (kMode == 1) {
+                if (lane == 0) prefetch_l2(ahead, kSlot);          // `ahead` of lane 0 = start of the half
+            } else {
+                copy_async16<0>(ring_at + fill, ahead), copy_async16<kSub>(ring_at + fill, ahead + Subtile<T>::kVectors);
+                if constexpr (sizeof(T) == 4)     // second 128-bit vector of each fp32 subtile
+                    copy_async16<512>(ring_at + fill, ahead + 32), copy_async16<kSub + 512>(ring_at + fill, ahead + Subtile<T>::kVectors + 32);
+            }
             --to_fetch;
             if (kParts == 1 || fetch_part == 1)
                 ahead += nwarps * (kParts * kHalf) - (kParts - 1) * kHalf;
@@ -571,7 +605,7 @@ template <class Op, typename T> struct ForwardStream {
                 ahead += kHalf;
             fetch_part ^= 1;
         }
-        copy_async_commit();       // an empty group keeps the wait arithmetic uniform
+        if constexpr (kMode == 0) copy_async_commit();   // an empty group keeps the wait arithmetic uniform
     }
 
     // Before the operator builds its tables: the first two halves are already on their way.
@@ -583,6 +617,7 @@ template <class Op, typename T> struct ForwardStream {
         mine = me < nunits ? (int)((nunits - me + nwarps - 1) / nwarps) : 0;
         ring_at = ring + 16 * lane;
         ahead = reinterpret_cast<const uint4 *>(x) + me * (kParts * kHalf) + lane;
+        now = ahead;
         to_fetch = mine * kParts;
         fetch_part = 0;
         fill = 0, fetch();
@@ -603,11 +638,19 @@ template <class Op, typename T> struct ForwardStream {
 #pragma unroll
             for (int part = 0; part < kParts; ++part) {
                 typename Subtile<T>::Raw raw[H];
-                copy_async_wait<1>();
-                raw[0].a = lds128<0>(ring_at + slot), raw[1].a = lds128<512>(ring_at + slot);
-                // the slot read one half ago is the one to fill now (two ahead of this one, modulo 3)
-                fill = slot == 0 ? 2 * kSlot : slot - kSlot;
-                slot = next_slot(slot);
+                if constexpr (kMode == 1) {
+                    // the half was requested into L2 two halves ago: these loads are L2 hits
+                    raw[0] = Subtile<T>::fetch(now), raw[1] = Subtile<T>::fetch(now + Subtile<T>::kVectors);
+                    now += (kParts == 1 || part == 1) ? y_step - (kParts - 1) * kHalf : kHalf;
+                } else {
+                    copy_async_wait<1>();
+                    raw[0].a = lds128<0>(ring_at + slot), raw[1].a = lds128<kSub>(ring_at + slot);
+                    if constexpr (sizeof(T) == 4)
+                        raw[0].b = lds128<512>(ring_at + slot), raw[1].b = lds128<kSub + 512>(ring_at + slot);
+                    // the slot read one half ago is the one to fill now (two ahead of this one, modulo 3)
+                    fill = slot == 0 ? 2 * kSlot : slot - kSlot;
+                    slot = next_slot(slot);
+                }
                 fetch();
                 if (part == 0)
                     forward_half<Op, T, S, kExact, 0, 0, H>(op, scratch, raw, yl, put_at, lane);
@@ -616,7 +659,7 @@ template <class Op, typename T> struct ForwardStream {
             }
             S::flush(strip, out, lane);
         }
-        copy_async_wait<0>();
+        if constexpr (kMode == 0) copy_async_wait<0>();
     }
 };
 
@@ -629,12 +672,13 @@ __global__ void __launch_bounds__(kThreads, MINB) forward_tiles_kernel(const T *
     constexpr int kStrip = Stager<T, B, kStaged>::kBytes > Stager<T, B, 1>::kBytes ? Stager<T, B, kStaged>::kBytes
                                                                                     : Stager<T, B, 1>::kBytes;
     __shared__ alignas(16) uint8_t strips[kWarps][(kStrip + 15) / 16 * 16];
-    __shared__ alignas(16) uint8_t rings[kRing ? kWarps : 1][kRing ? 3 * 1024 : 16];   // cp.async input ring
+    extern __shared__ __align__(16) uint8_t rings[];       // cp.async input ring: ring_bytes<Op, T, U>() at launch
     __shared__ typename Op::Scratch scratch;
     const uint32_t strip = (uint32_t)__cvta_generic_to_shared(strips[threadIdx.x >> 5]);
     if constexpr (kRing) {
         ForwardStream<Op, T> stream;
-        stream.start(x, ntiles * 2, (uint32_t)__cvta_generic_to_shared(rings[threadIdx.x >> 5]));
+        stream.start(x, ntiles * 2, (uint32_t)__cvta_generic_to_shared(rings) +
+                                        (threadIdx.x >> 5) * (uint32_t)(ring_bytes<Op, T, U>() / kWarps));
         op.prepare(scratch);       // table set-up overlaps the first loads
         if (op.exact())
             stream.template run<true>(op, scratch, y, state, strip);

@@ -15,6 +15,7 @@ i.e. the same ``S`` in every layer and step), and ``S`` is created in the input 
 """
 from __future__ import annotations
 
+import contextlib
 import weakref
 
 from typing import Literal, Optional
@@ -180,6 +181,9 @@ class _SharedSketch:
             tensor.__dict__.pop(cls.ATTRIBUTE, None)
 
 
+_NO_CONTEXT = contextlib.nullcontext()
+
+
 def _autocast_operands(input_view: T.Tensor, weight: T.Tensor, bias: Optional[T.Tensor]):
     """``F.linear`` would be autocast; the ``out=`` product that replaces it is not (and raises on
     mixed dtypes), so the operands are cast here the way autocast would."""
@@ -213,8 +217,9 @@ class LinearGRPFunc(T.autograd.Function):
         ctx.proj_features = proj_features
         ctx.matmul = matmul
         ctx.stream = ctx.generator_state = ctx.shared_input = None
-        ctx.autocast = (T.is_autocast_enabled(input.device.type), T.get_autocast_dtype(input.device.type))
-        lhs, rhs, offset_term = _autocast_operands(input_view, weight, bias)
+        ctx.autocast = T.get_autocast_dtype(input.device.type) if T.is_autocast_enabled(input.device.type) else None
+        lhs, rhs, offset_term = (input_view, weight, bias) if ctx.autocast is None else \
+            _autocast_operands(input_view, weight, bias)
 
         if not ctx.needs_input_grad[1]:
             # frozen weight / inference: nothing will ever read a sketch, so none is taken
@@ -250,12 +255,14 @@ class LinearGRPFunc(T.autograd.Function):
     def backward(ctx, grad_output):
         input_proj, weight, bias = ctx.saved_tensors
         grad_input = grad_weight = grad_bias = None
-        enabled, dtype = ctx.autocast
-        with T.autocast(grad_output.device.type, dtype=dtype, enabled=enabled):
+        # backward runs under the autocast state of forward (a context manager only when it was on:
+        # entering one costs ~10 us per layer)
+        with (T.autocast(grad_output.device.type, dtype=ctx.autocast) if ctx.autocast is not None else _NO_CONTEXT):
             if ctx.needs_input_grad[0]:
                 grad_input = grad_output @ weight
             if ctx.needs_input_grad[1] and ctx.stream is not None:
-                _SharedSketch.drop(ctx.shared_input)
+                if ctx.shared_input is not None:
+                    _SharedSketch.drop(ctx.shared_input)
                 grad_view = grad_output.reshape(-1, grad_output.shape[-1])
                 if _native_sketch_available(grad_view, ctx.matmul):
                     grad_proj = _native_sketch(grad_view, ctx.proj_features, *ctx.stream, ctx.matmul, 1.0)

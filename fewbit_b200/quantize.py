@@ -98,10 +98,12 @@ class _Integrals:
         return float(np.sum(np.diff(s2) - np.diff(f) ** 2 / np.diff(borders)))
 
 
-def _dynamic_programme(integ: _Integrals, levels: int, candidates: int) -> np.ndarray:
-    """Best `levels - 1` interior borders among `candidates` grid points (plus the domain ends)."""
-    idx = np.linspace(0, integ.x.size - 1, candidates + 2).round().astype(int)
-    idx = np.unique(np.concatenate([idx, np.searchsorted(integ.x, integ.jumps[1::2])]).astype(int))
+def _dynamic_programme(integ: _Integrals, levels: int, candidates: int, reach: float = np.inf) -> np.ndarray:
+    """Best `levels - 1` interior borders among `candidates` grid points (plus the domain ends);
+    interior borders are taken from |x| <= reach only."""
+    inside = np.nonzero(np.abs(integ.x) <= reach)[0]
+    idx = inside[np.linspace(0, inside.size - 1, candidates + 2).round().astype(int)]
+    idx = np.unique(np.concatenate([[0, integ.x.size - 1], idx, np.searchsorted(integ.x, integ.jumps[1::2])]).astype(int))
     x, f, s2 = integ.x[idx], integ.f[idx], integ.s2[idx]
     n = x.size
     with np.errstate(divide='ignore', invalid='ignore'):
@@ -120,7 +122,7 @@ def _dynamic_programme(integ: _Integrals, levels: int, candidates: int) -> np.nd
     return np.concatenate([[x[0]], x[np.array(cuts[::-1], dtype=int)], [x[-1]]])
 
 
-def _polish(integ: _Integrals, borders: np.ndarray, sweeps: int = 200) -> np.ndarray:
+def _polish(integ: _Integrals, borders: np.ndarray, sweeps: int = 200, reach: float = np.inf) -> np.ndarray:
     """Lloyd-Max: move each border to where f' equals the mean of the neighbouring levels."""
     func = integ.func
     best, best_err = borders.copy(), integ.error(borders)
@@ -139,7 +141,12 @@ def _polish(integ: _Integrals, borders: np.ndarray, sweeps: int = 200) -> np.nda
         gap = np.minimum(np.diff(best)[:-1], np.diff(best)[1:])
         move = np.clip(move, -0.45 * gap, 0.45 * gap)      # keep the order
         trial = best.copy()
-        trial[1:-1] = inner + step * move
+        trial[1:-1] = np.clip(inner + step * move, -reach, reach)
+        if np.any(np.diff(trial) <= 0):
+            step *= 0.5
+            if step < 1e-3:
+                break
+            continue
         err = integ.error(trial)
         if err < best_err * (1 - 1e-12):
             best, best_err = trial, err
@@ -150,14 +157,17 @@ def _polish(integ: _Integrals, borders: np.ndarray, sweeps: int = 200) -> np.nda
     return best
 
 
-def optimal_table(spec, bits: int, domain=DOMAIN, candidates: int = 2048):
+def optimal_table(spec, bits: int, domain=DOMAIN, candidates: int = 2048, reach: float = np.inf):
     """(borders, levels, error): float64 arrays in the built-in layout (borders include the domain
-    ends) minimising the reference's objective for 2**bits levels."""
+    ends) minimising the reference's objective for 2**bits levels.  `reach` confines the interior
+    borders to |x| <= reach (the outer pieces then run from there to the domain ends): derivatives
+    with heavy tails (softsign) otherwise place borders so far out that the kernels' uniform cell
+    look-up cannot separate the dense ones in the middle."""
     if not 1 <= bits <= 8:
         raise ValueError('bits must be in 1..8')
     _, func = _callable(spec)
     integ = _Integrals(func, domain)
-    borders = _polish(integ, _dynamic_programme(integ, 1 << bits, candidates))
+    borders = _polish(integ, _dynamic_programme(integ, 1 << bits, candidates, reach), reach=reach)
     f, _ = integ.at(borders)
     return borders, np.diff(f) / np.diff(borders), integ.error(borders)
 

@@ -55,8 +55,8 @@ def encode(border, k, bits):
     return pattern | low
 
 
-def build_words(bounds, bits):
-    cells = 16 << bits
+def build_words(bounds, bits, cells=None):
+    cells = cells or (2048 if bits == 6 else 16 << bits)
     cell = cell_map(bounds, cells)
     of_border = cell(bounds)
     words = np.zeros(cells, np.uint32)
@@ -72,13 +72,17 @@ def build_words(bounds, bits):
 @pytest.mark.parametrize('bits', [3, 4, 5, 6, 7, 8])
 def test_word_table_reproduces_the_bucket_search_for_every_bf16_value(bits):
     x = bf16_values()
-    checked = 0
+    checked = small = 0
     for name in CONTINOUS:
         borders, _ = store.get(name, bits, 'cpu', torch.bfloat16)
         bounds = borders[1:-1].float().numpy()
         if len(np.unique(bounds)) != len(bounds):
             continue        # borders that collide after the cast to bf16: the kernel's exact path
-        cell, words, crowded = build_words(bounds, bits)
+        # 3 and 4 bits: the kernel first tries 32 cells (one word per bank), then the full table
+        cell, words, crowded = build_words(bounds, bits, 32) if bits <= 4 else (None, None, True)
+        small += not crowded
+        if crowded:
+            cell, words, crowded = build_words(bounds, bits)
         if crowded:
             continue
         checked += 1
@@ -92,6 +96,8 @@ def test_word_table_reproduces_the_bucket_search_for_every_bf16_value(bits):
         for j in range(copies):
             np.testing.assert_array_equal((w >> (bits * j)) & ((1 << bits) - 1), w & ((1 << bits) - 1))
     assert checked >= 8, f'only {checked} tables exercised the word layout at {bits} bits'
+    if bits == 3:
+        assert small >= 10, f'only {small} of the 3-bit tables fit the conflict-free 32-cell table'
 
 
 def test_negative_zero_and_extreme_borders():
