@@ -475,23 +475,32 @@ def side_measurements(dev, peak, traffic_table):
     def timed(fn, reps=25, skip=5, group=3):
         """Median over reps of (time of `group` launches, one per buffer set) / group.  Before every
         group the L2 is flushed by reading 1 GiB; the launches of a group touch different buffers,
-        so every one of them finds its inputs in HBM.  (Events around a single ~40 us launch add
-        ~2 us of their own; a group amortises that.)"""
+        so every one of them finds its inputs in HBM.  The group is replayed from a CUDA graph:
+        events around a single ~40 us launch add ~2 us of their own, and launches issued from
+        Python arrive later than a 40 us kernel ends on a slow host."""
+        for k in range(group):
+            fn(k)
+        torch.cuda.synchronize()
+        side, graph = torch.cuda.Stream(), torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for k in range(group):
+                    fn(k)
+        torch.cuda.synchronize()
         ts = []
         for it in range(reps):
             sink.copy_(flush.sum())
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            for k in range(group):
-                fn(k)
+            graph.replay()
             b.record()
             torch.cuda.synchronize()
             if it >= skip:
                 ts.append(a.elapsed_time(b) / group)
         return statistics.median(ts)
 
-    where = ('128x128x3072 elements; median of 20 groups of 3 launches on 3 distinct buffer sets, L2 flushed by '
-             'reading 1 GiB before each group (inputs always come from HBM)')
+    where = ('128x128x3072 elements; median of 20 groups of 3 launches on 3 distinct buffer sets (replayed from a '
+             'CUDA graph), L2 flushed by reading 1 GiB before each group (inputs always come from HBM)')
     for tag, dtype, es in (('f32', torch.float32, 4), ('bf16', torch.bfloat16, 2)):
         borders, levels = store.get('gelu', 3, dev, dtype)
         bounds = borders[1:-1].contiguous()

@@ -730,6 +730,11 @@ struct TanhshrinkFn {  // codec.cu:648-653
 #ifndef FEWBIT_PAIRS
 #define FEWBIT_PAIRS 1
 #endif
+// Functions whose bf16 formula is so short that streaming the input (tile.cuh, ForwardStream) costs
+// more in bookkeeping than the exposed load latency it removes, up to 4 bits (measured per function,
+// profiles/r02_stream_per_function.txt: hardswish 87 % without against 80 % with, sigmoid 85 / 80,
+// softsign 86 / 80; from 5 bits on streaming wins or ties everywhere).
+template <class Fn> struct is_light_bf16 : std::false_type {};
 template <class Fn, typename = void> struct has_pairs : std::false_type {};
 template <class Fn> struct has_pairs<Fn, std::enable_if_t<Fn::kPaired>> : std::true_type {};
 template <class Fn, typename = void> struct has_pairs32 : std::false_type {};
@@ -764,10 +769,15 @@ FEWBIT_TILE_HINT_F32(SiluFn, 2, 3, 0)
 FEWBIT_TILE_HINT_F32(SoftplusFn, 2, 3, 1)
 #undef FEWBIT_TILE_HINT_F32
 
+template <> struct is_light_bf16<HardswishFn> : std::true_type {};
+template <> struct is_light_bf16<SigmoidFn> : std::true_type {};
+template <> struct is_light_bf16<SoftsignFn> : std::true_type {};
+
 template <class Fn, typename T, int B> struct QuantizeOp {
     static constexpr int kBits = B;
     static constexpr int kSubtilesF32 = TileHintF32<Fn>::kSubtiles, kMinBlocksF32 = TileHintF32<Fn>::kMinBlocks;
     static constexpr bool kStreamF32 = TileHintF32<Fn>::kStream && B >= 3;   // 1-2 bits: measured slower (89 -> 81 %)
+    static constexpr bool kStreamInput = !(sizeof(T) == 2 && is_light_bf16<Fn>::value && B <= 4);
     static constexpr bool kHeavy = true;  // transcendental math: see TileConfig in launch.cuh
     using Scratch = typename Bucketizer<T, B>::Scratch;
     Fn fn;

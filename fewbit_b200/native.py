@@ -57,6 +57,8 @@ def lib() -> C.CDLL:
                                f'__graft_entry__ as g; g.build()"` or `make -C fewbit_b200/csrc`.')
         handle = C.CDLL(str(LIBRARY))
         for name, (restype, argtypes) in PROTOTYPES.items():
+            if not hasattr(handle, name) and 'FEWBIT_B200_LIBRARY' in os.environ:
+                continue        # tuning runs against an older build of the kernels
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = restype, argtypes
         _lib = handle
