@@ -76,15 +76,14 @@ namespace sketch {
 #define FEWBIT_SKETCH_THREADS 512
 #endif
 constexpr int kThreads = FEWBIT_SKETCH_THREADS;     // warp 0: TMA, warp 1: MMA, the rest generate S
-constexpr int kStages = 3;
-constexpr int kBlockK = 64;            // tokens per stage
+constexpr int kBlockK = 64;            // tokens per stage (four K = 16 MMAs per feature block)
 constexpr int kFeaturesPerCta = 384;   // 3 MMA M-blocks of 128
 constexpr int kMaxRows = 160;          // BN: sketch rows per CTA (TMEM: 3 * 160 <= 512 columns)
 constexpr int kBoxBytes = 64 * 64 * 2;                        // one TMA box: 64 tokens x 64 features
-constexpr int kXStageBytes = (kFeaturesPerCta / 64) * kBoxBytes;   // 49152
-constexpr int kSStageBytes = kMaxRows * 128;                  // 20480: BN rows x 64 bf16
-constexpr int kStageBytes = kXStageBytes + kSStageBytes;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* alignment */ + 256 /* barriers */;
+constexpr int kUnitBytes = 2 * kBoxBytes;                     // X ring entry: 64 tokens x 128 features
+constexpr int kMaxUnits = 12, kMaxSlots = 4;                  // ring sizes are chosen at launch (shared memory)
+constexpr int kBarrierBytes = 512;
+constexpr int kSmemLimit = 232448;                            // 227 KB per CTA
 constexpr int kGeneratorWarps = kThreads / 32 - 2;
 constexpr int kGeneratorThreads = kGeneratorWarps * 32;
 constexpr int kTmemColumns = 512;
@@ -124,13 +123,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         "l"(map), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const CUtensorMap *map, int c0, int c1,
-                                                      uint32_t bar, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
-        "[%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
-        "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
-        : "memory");
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1) {   // into L2 only
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1)
+                 : "memory");
 }
 // kPair selects the two-SM forms (cta_group::2): one MMA spans the CTA pair of a cluster, M = 256.
 template <bool kPair>
@@ -356,11 +351,14 @@ struct Params {
     float scale;         // applied here only when split_k == 1
     uint32_t seed_lo, seed_hi, off_lo, off_hi;
     int kind;
-    int cluster_x;       // CTAs along grid.x that share X tiles (TMA multicast)
-    int cluster_y;       // CTAs along grid.y that share one generated S tile
+    int cluster_y;       // CTAs along grid.y that share one generated S slot
+    int x_units;         // X ring: entries of 64 tokens x 128 features
+    int s_slots;         // S ring: entries of 128 tokens x (my share of) BN rows
+    int s_tile_bytes;    // one 64-token half of an S slot
+    int prefetch;        // stages ahead that the TMA warp pulls X into L2 (0 = off)
     unsigned long long *trace;   // FEWBIT_B200_SKETCH_TRACE: per-role time stamps of CTA (0,0,0), else null
     int debug;           // timing experiments only (results are garbage): 1 = skip generating S,
-                         // 2 = skip loading X, 4 = skip issuing MMAs, 16 = declare A K-major
+                         // 4 = skip issuing MMAs
 };
 
 template <bool kPair>
@@ -369,8 +367,11 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzled tiles need 1024-byte alignment.
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * kStages + 1);
+    const int units = prm.x_units, slots = prm.s_slots;
+    const uint32_t tile_bytes = (uint32_t)prm.s_tile_bytes;          // one 64-token half of an S slot
+    uint8_t *s_ring = smem + units * kUnitBytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_ring + slots * 2 * tile_bytes);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kMaxUnits + 2 * kMaxSlots + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool traced = prm.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
@@ -379,35 +380,38 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     const int p0 = (kPair ? blockIdx.y : blockIdx.x) * prm.block_rows;
     const int d0 = (kPair ? blockIdx.x : blockIdx.y) * kFeaturesPerCta;
     const int bn = prm.block_rows;
-    const int nblocks = min(3, (prm.features - d0 + 127) / 128);   // 128-feature MMA blocks
+    const int nblocks = min(3, (prm.features - d0 + 127) / 128);   // 128-feature MMA blocks = X units per stage
     const int nboxes = min(6, (prm.features - d0 + 63) / 64);
     const int64_t total_kb = (prm.tokens + kBlockK - 1) / kBlockK;
-    const int64_t kb_begin = (int64_t)blockIdx.z * prm.kblocks_per_split;
+    const int64_t kb_begin = (int64_t)blockIdx.z * prm.kblocks_per_split;      // even: S slots span two k-blocks
     const int64_t kb_end = min(total_kb, kb_begin + prm.kblocks_per_split);
     const int iters = (int)max((int64_t)0, kb_end - kb_begin);
 
-    auto full_x = [&](int s) { return smem_addr(bars + s); };
-    auto full_s = [&](int s) { return smem_addr(bars + kStages + s); };
-    auto empty = [&](int s) { return smem_addr(bars + 2 * kStages + s); };
-    const uint32_t accum_full = smem_addr(bars + 3 * kStages);
-    auto x_stage = [&](int s) { return smem_addr(smem + s * kStageBytes); };
-    auto s_stage = [&](int s) { return smem_addr(smem + s * kStageBytes + kXStageBytes); };
+    auto full_x = [&](int u) { return smem_addr(bars + u); };
+    auto empty_x = [&](int u) { return smem_addr(bars + kMaxUnits + u); };
+    auto full_s = [&](int j) { return smem_addr(bars + 2 * kMaxUnits + j); };
+    auto empty_s = [&](int j) { return smem_addr(bars + 2 * kMaxUnits + kMaxSlots + j); };
+    const uint32_t accum_full = smem_addr(bars + 2 * kMaxUnits + 2 * kMaxSlots);
+    const uint32_t x_ring = smem_addr(smem);
 
-    const int cx = prm.cluster_x, cy = prm.cluster_y, cluster = cx * cy;
-    const uint32_t rx = !kPair && cx > 1 ? cluster_cta_x() : 0;                           // rank = rx + ry * cx
-    const uint32_t ry = kPair ? cluster_cta_x() : (cy > 1 ? cluster_cta_y() : 0);           // which share of S is mine
-    const int my_rows = bn / cy;                            // rows of each S tile this CTA generates
-    // Pair mode (cluster 1 x 2, cta_group::2): the two CTAs own the two 384-feature halves of a
-    // 768-feature slab and HALF of every S tile each; one M = 256 MMA, issued by the leader (ry = 0),
+    const int cy = prm.cluster_y;                            // CTAs that share one generated S slot
+    const uint32_t ry = kPair ? cluster_cta_x() : (cy > 1 ? cluster_cta_y() : 0);   // which share of S is mine
+    const int my_rows = bn / cy;                             // rows of each S slot this CTA generates
+    const bool pushing = !kPair && cy > 1;                   // my block also goes to the y-peer's shared memory
+    // Pair mode (cluster 2 x 1, cta_group::2): the two CTAs own the two 384-feature halves of a
+    // 768-feature slab and HALF of every S slot each; one M = 256 MMA, issued by the leader (ry = 0),
     // reads X^T from both shared memories and each half of S once for both.  The leader's full_x
     // counts the TMA bytes of both CTAs, its full_s the generator warps of both.
     const bool leader = !kPair || ry == 0;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(full_x(s), 1);
-            // own generator warps, + the peer's forwarded arrival (pair leader) or the expect_tx arrival (cy > 1)
-            mbar_init(full_s(s), kGeneratorWarps + ((kPair ? ry == 0 : cy > 1) ? 1 : 0));
-            mbar_init(empty(s), kPair ? 1 : cluster);                   // one commit per issuing CTA
+        for (int u = 0; u < units; ++u) {
+            mbar_init(full_x(u), 1);
+            mbar_init(empty_x(u), kPair ? 1 : cy);                      // one commit per issuing CTA
+        }
+        for (int j = 0; j < slots; ++j) {
+            // own generator warps, + the peer's forwarded arrival (pair leader) or the expect_tx arrival (pushing)
+            mbar_init(full_s(j), kGeneratorWarps + ((kPair ? ry == 0 : cy > 1) ? 1 : 0));
+            mbar_init(empty_s(j), kPair ? 1 : cy);
         }
         mbar_init(accum_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -427,93 +431,107 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (cluster > 1) cluster_sync();          // peers' barriers exist before anyone signals them
+    if (kPair || cy > 1) cluster_sync();      // peers' barriers exist before anyone signals them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     if (traced && threadIdx.x == 0) prm.trace[1] = now_ns();
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer ----
+        // One ring entry ("unit") = the two 64-feature boxes of one MMA block: 16 KB.  A stage (64 tokens)
+        // takes `nblocks` consecutive units; each is released by its own commit, so the ring refills
+        // at a third of a stage's granularity and need not hold a whole number of stages.
+        int u = 0;
+        uint32_t phase = 0;
         for (int it = 0; it < iters; ++it) {
-            const int s = it % kStages;
-            mbar_wait(empty(s), ((it / kStages) & 1) ^ 1);
             const int token = (int)((kb_begin + it) * kBlockK);
-            if (elect_one()) {
-                if (prm.debug & 2) {
-                    if (leader) mbar_arrive(full_x(s));
-                } else if constexpr (kPair) {
-                    if (leader) mbar_expect_tx(full_x(s), 2 * nboxes * kBoxBytes);     // both CTAs' boxes
-                    const uint32_t bar = map_to_cta(full_x(s), 0);
-                    for (int b = 0; b < nboxes; ++b)
-                        tma_load_2d_pair(x_stage(s) + b * kBoxBytes, &x_map, d0 + 64 * b, token, bar);
-                } else {
-                    mbar_expect_tx(full_x(s), nboxes * kBoxBytes);                     // all boxes, whoever loads them
-                    if (cy > 1) mbar_expect_tx(full_s(s), (cy - 1) * my_rows * 128);   // the y-peer's block
-                    if (cx > 1) {
-                        const uint16_t mask = (uint16_t)(((1u << cx) - 1u) << (ry * cx));  // my row of the cluster
-                        for (int b = (int)rx; b < nboxes; b += cx)
-                            tma_load_2d_multicast(x_stage(s) + b * kBoxBytes, &x_map, d0 + 64 * b, token, full_x(s), mask);
+            if (prm.prefetch > 0 && it + prm.prefetch < iters && elect_one())
+                for (int b = 0; b < nboxes; ++b)
+                    tma_prefetch_2d(&x_map, d0 + 64 * b, token + prm.prefetch * kBlockK);
+            for (int m = 0; m < nblocks; ++m) {
+                mbar_wait(empty_x(u), phase ^ 1);
+                if (elect_one()) {
+                    const int boxes = min(2, nboxes - 2 * m);
+                    const uint32_t dst = x_ring + u * kUnitBytes;
+                    if constexpr (kPair) {
+                        if (leader) mbar_expect_tx(full_x(u), 2 * boxes * kBoxBytes);     // both CTAs' boxes
+                        const uint32_t bar = map_to_cta(full_x(u), 0);
+                        for (int b = 0; b < boxes; ++b)
+                            tma_load_2d_pair(dst + b * kBoxBytes, &x_map, d0 + 128 * m + 64 * b, token, bar);
                     } else {
-                        for (int b = 0; b < nboxes; ++b)
-                            tma_load_2d(x_stage(s) + b * kBoxBytes, &x_map, d0 + 64 * b, token, full_x(s));
+                        mbar_expect_tx(full_x(u), boxes * kBoxBytes);
+                        for (int b = 0; b < boxes; ++b)
+                            tma_load_2d(dst + b * kBoxBytes, &x_map, d0 + 128 * m + 64 * b, token, full_x(u));
                     }
                 }
+                __syncwarp();
+                if (++u == units) u = 0, phase ^= 1;
             }
-            __syncwarp();
         }
     } else if (warp == 1) {
         // -------------------------------------------------------------- MMA issuer ----
         if (leader) {   // the whole warp walks the pipeline; one elected lane issues (see elect_one)
             // cute::UMMA::InstrDescriptor: D = f32, A = B = bf16, A MN-major, B K-major, N, M = 128
             // per CTA (256 across the pair).
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((prm.debug & 16) ? 0u : (1u << 15)) | (0u << 16) |
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (0u << 16) |
                                    ((uint32_t)(bn >> 3) << 17) | (((kPair ? 256u : 128u) >> 4) << 24);
             // Shared-memory descriptors differ only in the 14-bit address field of their low word:
             //   A: 64-feature groups 8192 B apart (LBO), 8-token groups 1024 B apart (SBO); +2048 B per
-            //      16 tokens; 128 features = two boxes.
+            //      16 tokens; one unit = 128 features.
             //   B: rows of 128 B (64 tokens), 8-row groups 1024 B apart (SBO); +32 B per 16 tokens.
             const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-            const uint32_t a_lo = ((x_stage(0) & 0x3FFFFu) >> 4) | ((uint32_t)(kBoxBytes >> 4) << 16);
-            const uint32_t b_lo = ((s_stage(0) & 0x3FFFFu) >> 4) | ((16u >> 4) << 16);
+            const uint32_t a_lo = ((x_ring & 0x3FFFFu) >> 4) | ((uint32_t)(kBoxBytes >> 4) << 16);
+            const uint32_t b_lo = ((smem_addr(s_ring) & 0x3FFFFu) >> 4) | ((16u >> 4) << 16);
             const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base, 0);
             const bool skip_mma = (prm.debug & 4) != 0;
             unsigned long long wait_x = 0, wait_s = 0;
+            int u = 0, j = 0;
+            uint32_t phase = 0, sphase = 0;
             for (int it = 0; it < iters; ++it) {
-                const int s = it % kStages;
-                const uint32_t parity = (it / kStages) & 1;
-                const unsigned long long w0 = traced ? now_ns() : 0;
-                mbar_wait(full_x(s), parity);
-                const unsigned long long w1 = traced ? now_ns() : 0;
-                if constexpr (kPair) mbar_wait_cluster(full_s(s), parity);   // the peer's generators wrote its half
-                else mbar_wait(full_s(s), parity);
-                if (traced && lane == 0) {
-                    const unsigned long long w2 = now_ns();
-                    wait_x += w1 - w0, wait_s += w2 - w1;
-                    if (it == 0) prm.trace[2] = w2;
+                const int half = it & 1;
+                if (half == 0) {
+                    const unsigned long long w0 = traced ? now_ns() : 0;
+                    if constexpr (kPair) mbar_wait_cluster(full_s(j), sphase);   // the peer's generators wrote its half
+                    else mbar_wait(full_s(j), sphase);
+                    if (traced && lane == 0) wait_s += now_ns() - w0;
                 }
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (elect_one()) {
-                    const uint32_t stage_off = (uint32_t)s * (uint32_t)(kStageBytes >> 4);
-                    if (!skip_mma) {
+                const uint32_t b_tile = b_lo + (uint32_t)(((uint32_t)(2 * j + half) * tile_bytes) >> 4);
+                for (int m = 0; m < nblocks; ++m) {
+                    const unsigned long long w0 = traced ? now_ns() : 0;
+                    mbar_wait(full_x(u), phase);
+                    if (traced && lane == 0) {
+                        const unsigned long long w1 = now_ns();
+                        wait_x += w1 - w0;
+                        if (it == 0 && m == 0) prm.trace[2] = w1;
+                    }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        if (!skip_mma) {
+                            const uint32_t a_unit = a_lo + (uint32_t)u * (uint32_t)(kUnitBytes >> 4);
 #pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k) {
-                            const uint64_t desc_b = ((uint64_t)desc_hi << 32) | (b_lo + stage_off + 2u * k);
-#pragma unroll
-                            for (int m = 0; m < 3; ++m) {
-                                if (m < nblocks) {
-                                    const uint64_t desc_a = ((uint64_t)desc_hi << 32) |
-                                                            (a_lo + stage_off + (uint32_t)((m * 2 * kBoxBytes + 2048 * k) >> 4));
-                                    umma_bf16<kPair>(tmem + m * kMaxRows, desc_a, desc_b, idesc, (it | k) != 0);
-                                }
+                            for (int k = 0; k < kBlockK / 16; ++k) {
+                                const uint64_t desc_a = ((uint64_t)desc_hi << 32) | (a_unit + (uint32_t)((2048 * k) >> 4));
+                                const uint64_t desc_b = ((uint64_t)desc_hi << 32) | (b_tile + 2u * k);
+                                umma_bf16<kPair>(tmem + m * kMaxRows, desc_a, desc_b, idesc, (it | k) != 0);
                             }
                         }
+                        // the unit is reusable once these MMAs have read it -- in every CTA of the cluster
+                        if constexpr (kPair) umma_commit_pair(empty_x(u));
+                        else if (cy > 1) umma_commit_cluster(empty_x(u), (uint16_t)((1u << cy) - 1));
+                        else umma_commit(empty_x(u));
                     }
-                    // smem slot reusable once these MMAs have read it -- in every CTA of the cluster
-                    if constexpr (kPair) umma_commit_pair(empty(s));
-                    else if (cluster > 1) umma_commit_cluster(empty(s), (uint16_t)((1u << cluster) - 1));
-                    else umma_commit(empty(s));
+                    __syncwarp();
+                    if (++u == units) u = 0, phase ^= 1;
                 }
-                __syncwarp();
+                if (half == 1 || it == iters - 1) {       // both halves of the S slot consumed
+                    if (elect_one()) {
+                        if constexpr (kPair) umma_commit_pair(empty_s(j));
+                        else if (cy > 1) umma_commit_cluster(empty_s(j), (uint16_t)((1u << cy) - 1));
+                        else umma_commit(empty_s(j));
+                    }
+                    __syncwarp();
+                    if (++j == slots) j = 0, sphase ^= 1;
+                }
             }
             if (elect_one()) {   // accumulators complete (in both CTAs of a pair)
                 if constexpr (kPair) umma_commit_pair(accum_full);
@@ -522,72 +540,73 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
             __syncwarp();
             if (traced && lane == 0) prm.trace[3] = now_ns(), prm.trace[6] = wait_x, prm.trace[7] = wait_s;
         } else {
-            // Pair mode, second CTA: forward "my half of S is written" to the leader's barrier.  The
-            // cluster-scope release costs ~0.5 us; paid here, on an otherwise idle warp, it stays off
-            // the generators' critical path.
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % kStages;
-                mbar_wait(full_s(s), (it / kStages) & 1);
-                if (elect_one()) mbar_arrive_cluster(map_to_cta(full_s(s), 0));
+            // Pair mode, second CTA: forward "my half of the S slot is written" to the leader's barrier.
+            // The cluster-scope release costs ~0.5 us; paid here, on an otherwise idle warp, it stays
+            // off the generators' critical path.
+            int j = 0;
+            uint32_t sphase = 0;
+            for (int n = 0; n < (iters + 1) / 2; ++n) {
+                mbar_wait(full_s(j), sphase);
+                if (elect_one()) mbar_arrive_cluster(map_to_cta(full_s(j), 0));
                 __syncwarp();
+                if (++j == slots) j = 0, sphase ^= 1;
             }
         }
     } else {
         // -------------------------------------------------------------- generators ----
+        // One S slot = 128 tokens = two K-major SW128 tiles of 64 tokens; the generators run up to
+        // `slots` slots ahead of the MMAs, independently of the X ring.
         const Philox rng{prm.seed_lo, prm.seed_hi};
-        const int gt = threadIdx.x - 64;                       // 0 .. 447
+        const int gt = threadIdx.x - 64;
         unsigned long long wait_e = 0, busy = 0;
         long long ph[4] = {0, 0, 0, 0};      // cycles: generate + store, proxy fence, block sync + push, arrive
-        for (int it = 0; it < iters; ++it) {
-            const int s = it % kStages;
+        const int row0 = (int)ry * my_rows;                // this CTA's block of the slot
+        const int place = kPair ? 0 : row0;                // pair mode: the block sits at the tile start
+        int j = 0;
+        uint32_t sphase = 0;
+        const int nslots = (iters + 1) / 2;
+        for (int n = 0; n < nslots; ++n) {
             const unsigned long long w0 = traced && gt == 0 ? now_ns() : 0;
-            mbar_wait(empty(s), ((it / kStages) & 1) ^ 1);
+            mbar_wait(empty_s(j), sphase ^ 1);
             const unsigned long long g0 = traced && gt == 0 ? now_ns() : 0;
             const long long c0 = traced && gt == 0 ? clock64() : 0;
             if (traced && gt == 0) wait_e += g0 - w0;
-            uint8_t *tile = smem + s * kStageBytes + kXStageBytes;
-            const int64_t kb = kb_begin + it;
-            const int row0 = (int)ry * my_rows;                // this CTA's block of the tile
-            const int place = kPair ? row0 : 0;                // pair mode: the block sits at the tile start
+            if (pushing && gt == 0) mbar_expect_tx(full_s(j), (uint32_t)((cy - 1) * my_rows * 128 * 2));   // the y-peer's block
+            uint8_t *slot = s_ring + (size_t)j * 2 * tile_bytes;
+            const int64_t kb = kb_begin + 2 * n;
+            auto chunk_at = [&](int r, int o) {     // row r of the tile, 16-byte chunk o of the slot's 256-byte row
+                return slot + (o >> 3) * tile_bytes + (r >> 3) * 1024 + (r & 7) * 128 + (((o & 7) ^ (r & 7)) << 4);
+            };
             if (prm.debug & 1) {
             } else if (prm.kind == 0) {
-                // One Philox call = 8 normals = one 16-byte chunk of a 128-byte K-major row.
-                // K-major SW128: chunk index XOR (row mod 8).  Up to 3 chunks per thread
-                // (160 rows x 8 chunks over 448 threads), independent chains interleave.
-                const int chunks = my_rows * 8;
-                auto put = [&](int i, const uint4 &v) {
-                    const int r = row0 - place + (i >> 3), o = i & 7;
-                    *reinterpret_cast<uint4 *>(tile + (r >> 3) * 1024 + (r & 7) * 128 + ((o ^ (r & 7)) << 4)) = v;
-                };
-                // chunks i and i + G together while both exist (two interleaved chains), then at most one
+                // One Philox call = 8 normals = one 16-byte chunk; 16 chunks per row and slot.
+                // Chunks i and i + G together while both exist (two interleaved chains), then at most one.
+                const int chunks = my_rows * 16;
+                auto put = [&](int i, const uint4 &v) { *reinterpret_cast<uint4 *>(chunk_at(place + (i >> 4), i & 15)) = v; };
                 int i = gt;
                 for (; i + kGeneratorThreads < chunks; i += 2 * kGeneratorThreads) {
                     const int i1 = i + kGeneratorThreads;
                     uint4 v0, v1;
-                    normal_octet2(rng, (uint32_t)(kb * 8 + (i & 7)), (uint32_t)(p0 + row0 + (i >> 3)),
-                                  (uint32_t)(kb * 8 + (i1 & 7)), (uint32_t)(p0 + row0 + (i1 >> 3)), prm.off_lo,
+                    normal_octet2(rng, (uint32_t)(kb * 8 + (i & 15)), (uint32_t)(p0 + row0 + (i >> 4)),
+                                  (uint32_t)(kb * 8 + (i1 & 15)), (uint32_t)(p0 + row0 + (i1 >> 4)), prm.off_lo,
                                   prm.off_hi, v0, v1);
                     put(i, v0), put(i1, v1);
                 }
                 if (i < chunks)
-                    put(i, normal_octet(rng, (uint32_t)(kb * 8 + (i & 7)), (uint32_t)(p0 + row0 + (i >> 3)), prm.off_lo,
+                    put(i, normal_octet(rng, (uint32_t)(kb * 8 + (i & 15)), (uint32_t)(p0 + row0 + (i >> 4)), prm.off_lo,
                                         prm.off_hi));
             } else {
-                // One Philox call = 128 signs; a 64-token stage uses half of it (two words), and
-                // each task expands one word = 32 tokens = four 16-byte chunks of a row, so that
-                // 2 x rows tasks keep most generator threads busy (the call is recomputed by the
-                // two tasks of a row: cheaper than leaving 3/4 of the threads idle).
-                for (int task = gt; task < 2 * my_rows; task += kGeneratorThreads) {
-                    const int row = row0 + (task >> 1), half = task & 1;
-                    const uint4 w = sign_block(rng, (uint32_t)(kb >> 1), (uint32_t)(p0 + row), prm.off_lo, prm.off_hi);
-                    const uint32_t word = (kb & 1) ? (half ? w.w : w.z) : (half ? w.y : w.x);
-                    const int r = row - place;
-                    uint8_t *base = tile + (r >> 3) * 1024 + (r & 7) * 128;
+                // One Philox call = 128 signs = one row of the slot.  A task expands one of its four words
+                // (32 tokens = four chunks); the four tasks of a row repeat the call in neighbouring lanes,
+                // which costs nothing in a SIMT warp and keeps 4 x rows threads busy.
+                for (int task = gt; task < 4 * my_rows; task += kGeneratorThreads) {
+                    const int row = task >> 2, q = task & 3;
+                    const uint4 w = sign_block(rng, (uint32_t)(kb >> 1), (uint32_t)(p0 + row0 + row), prm.off_lo, prm.off_hi);
+                    const uint32_t word = q == 0 ? w.x : q == 1 ? w.y : q == 2 ? w.z : w.w;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const uint32_t bits = word >> (c * 8);
-                        const int o = half * 4 + c;
-                        *reinterpret_cast<uint4 *>(base + ((o ^ (r & 7)) << 4)) =
+                        *reinterpret_cast<uint4 *>(chunk_at(place + row, q * 4 + c)) =
                             make_uint4(sign_pair(bits), sign_pair(bits >> 2), sign_pair(bits >> 4), sign_pair(bits >> 6));
                     }
                 }
@@ -595,30 +614,32 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
             const long long c1 = traced && gt == 0 ? clock64() : 0;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
             const long long c2 = traced && gt == 0 ? clock64() : 0;
-            if (!kPair && cy > 1) {
-                // all generator threads have written (and fenced) this CTA's block: push it to the y-peers
+            if (pushing) {
+                // all generator threads have written (and fenced) this CTA's block: push both halves to the y-peers
                 asm volatile("bar.sync 1, %0;" ::"n"(kGeneratorThreads) : "memory");
                 if (gt == 0) {
-                    const uint32_t block = smem_addr(tile) + row0 * 128;
                     for (uint32_t y = 0; y < (uint32_t)cy; ++y)
                         if (y != ry)
-                            bulk_copy_to_peer(map_to_cta(block, rx + y * cx), block, my_rows * 128,
-                                              map_to_cta(full_s(s), rx + y * cx));
+                            for (uint32_t h = 0; h < 2; ++h) {
+                                const uint32_t block = smem_addr(slot) + h * tile_bytes + row0 * 128;
+                                bulk_copy_to_peer(map_to_cta(block, y), block, my_rows * 128, map_to_cta(full_s(j), y));
+                            }
                 }
             }
             __syncwarp();
             const long long c3 = traced && gt == 0 ? clock64() : 0;
             if (traced && gt == 0) ph[0] += c1 - c0, ph[1] += c2 - c1, ph[2] += c3 - c2;
             if (traced && gt == 0) busy += now_ns() - g0;
-            if (lane == 0) mbar_arrive(full_s(s));       // pair mode, second CTA: warp 1 forwards it
+            if (lane == 0) mbar_arrive(full_s(j));       // pair mode, second CTA: warp 1 forwards it
             if (traced && gt == 0) ph[3] += clock64() - c3;
+            if (++j == slots) j = 0, sphase ^= 1;
         }
         if (traced && gt == 0) prm.trace[8] = wait_e, prm.trace[9] = now_ns(), prm.trace[10] = busy;
         if (traced && gt == 0)
-            for (int j = 0; j < 4; ++j) prm.trace[11 + j] = (unsigned long long)(ph[j] / max(iters, 1));
+            for (int q = 0; q < 4; ++q) prm.trace[11 + q] = (unsigned long long)(ph[q] / max(nslots, 1));
     }
     // -------------------------------------------------------------------- epilogue ----
-    // All 16 warps: a warp reads the TMEM lanes of its quadrant (warp % 4); the four warps of a
+    // All warps: a warp reads the TMEM lanes of its quadrant (warp % 4); the warps of a
     // quadrant share its (feature block, 16-column) units.  For a fixed sketch row the 32 lanes
     // hold 32 consecutive features: every store instruction writes one 128-byte line.
     {
@@ -629,27 +650,27 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
         float *out = prm.out + (prm.split_k > 1 ? (int64_t)blockIdx.z * prm.rows * prm.features : 0);
         const float scale = prm.split_k > 1 ? 1.0f : prm.scale;
         const int units_per_block = bn / 16;
-        for (int u = warp >> 2; u < nblocks * units_per_block; u += kThreads / 128) {
-            const int m = u / units_per_block, c = (u % units_per_block) * 16;
+        for (int t = warp >> 2; t < nblocks * units_per_block; t += kThreads / 128) {
+            const int m = t / units_per_block, c = (t % units_per_block) * 16;
             const int d = d0 + m * 128 + quarter * 32 + lane;
             uint32_t v[16];
             tmem_load16(tmem_base + ((uint32_t)(quarter * 32) << 16) + m * kMaxRows + c, v);
             if (iters == 0) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = 0;
+                for (int q = 0; q < 16; ++q) v[q] = 0;
             }
             if (d < prm.features) {
                 float *dst = out + (int64_t)(p0 + c) * prm.features + d;
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (p0 + c + j < prm.rows) dst[(int64_t)j * prm.features] = __uint_as_float(v[j]) * scale;
+                for (int q = 0; q < 16; ++q)
+                    if (p0 + c + q < prm.rows) dst[(int64_t)q * prm.features] = __uint_as_float(v[q]) * scale;
             }
         }
     }
     if (traced && warp == 4 && lane == 0) prm.trace[5] = now_ns();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (cluster > 1) cluster_sync();          // nobody leaves while peers may still signal it
+    if (kPair || cy > 1) cluster_sync();      // nobody leaves while peers may still signal it
     if (warp == 1) {
         if constexpr (kPair)
             asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -713,42 +734,49 @@ static EncodeTiled encode_tiled() {
     return fn;
 }
 
-// Pick the cluster (Cx row tiles sharing X by TMA multicast, Cy feature tiles sharing one
-// generated S tile), BN (multiple of 16 and of 8 Cy, <= 160) and split_k: minimise
-// waves * (time of one CTA).  Measured on B200 (profiles/r01_sketch_kernel.md): clusters of 8
-// along y lose to independent CTAs at D = 3072 (8-CTA placement leaves SMs idle and the lock-step
-// `empty` barrier couples eight pipelines), so both axes are capped at 2.
-static void plan(int rows, int features, int64_t tokens, int kind, int sms, int &bn, int &split_k, int &cx,
-                 int &cy, bool &pair) {
+// Pick how CTAs share a generated S slot (Cy feature tiles, or a cta_group::2 pair), BN (multiple of
+// 16 and of 8 Cy, <= 160) and split_k: minimise waves * (time of one CTA).  Measured on B200
+// (profiles/r01_sketch_kernel.md): clusters of 8 along y lose to independent CTAs at D = 3072 (8-CTA
+// placement leaves SMs idle and the lock-step `empty` barriers couple eight pipelines), and sharing X
+// between row tiles by TMA multicast loses too (L2 is not the limiter), so Cy <= 2 and X is not shared.
+struct Plan {
+    int bn, split_k, cy;
+    bool pair;
+    int kblocks_per_split;       // even: an S slot spans two 64-token stages
+    int x_units, s_slots, s_tile_bytes, smem_bytes;
+};
+
+static int env_int(const char *name, int fallback) {
+    const char *env = std::getenv(name);
+    return env ? std::atoi(env) : fallback;
+}
+
+static Plan plan(int rows, int features, int64_t tokens, int kind, int sms) {
+    Plan pl{};
     const int dtiles = (features + kFeaturesPerCta - 1) / kFeaturesPerCta;
     const int64_t kblocks = std::max<int64_t>(1, (tokens + kBlockK - 1) / kBlockK);
     // Default from the A/B runs in profiles/r01_sketch_kernel.md: S sharing between the two feature
-    // tiles of D = 768 helps (133 -> 123 us); X multicast does not (159 us), L2 is not the limiter.
-    cy = dtiles == 2 ? 2 : 1;
-    cx = 1;
-    // Pair mode (cta_group::2 MMAs over a 1 x 2 cluster) whenever the feature tiles come in full
-    // pairs: each S tile is generated once per pair and read from shared memory once per pair.
+    // tiles of D = 768 helps (133 -> 123 us).
+    pl.cy = dtiles == 2 ? 2 : 1;
+    // Pair mode (cta_group::2 MMAs over a 2 x 1 cluster) whenever the feature tiles come in full
+    // pairs: each S slot is generated once per pair and read from shared memory once per pair.
     // Measured (profiles/r01_sketch_kernel.md): with Gaussian entries the kernel is bound by generating
     // S and the pair halves that work (D = 3072: 493 -> 406 us); with Rademacher entries it is bound by
     // the MMA pipeline, and the extra hop of the peer's "S ready" signal costs more than it saves.
-    pair = features % (2 * kFeaturesPerCta) == 0 && kind == 0;
-    if (const char *env = std::getenv("FEWBIT_B200_SKETCH_PAIR")) pair = pair && std::atoi(env) != 0;
-    if (pair) cy = 2;
-    if (const char *env = std::getenv("FEWBIT_B200_SKETCH_CLUSTER")) {   // A/B runs: "<cx><cy>", e.g. 11, 21, 12, 22
-        const int v = std::atoi(env);
-        if (v / 10 >= 1 && v / 10 <= 2) cx = rows > 160 ? v / 10 : 1;
-        if (v % 10 >= 1 && v % 10 <= 2) cy = std::min(cy, v % 10);
-        pair = false;
+    pl.pair = features % (2 * kFeaturesPerCta) == 0 && kind == 0;
+    pl.pair = pl.pair && env_int("FEWBIT_B200_SKETCH_PAIR", 1) != 0;
+    if (pl.pair) pl.cy = 2;
+    if (const int v = env_int("FEWBIT_B200_SKETCH_CLUSTER", 0)) {   // A/B runs: Cy without cta_group::2
+        if (v >= 1 && v <= 2) pl.cy = std::min(pl.cy, v);
+        pl.pair = false;
     }
     double best = 1e300;
-    bn = 64, split_k = 1;
-    int only_bn = 0, only_sk = 0;
-    if (const char *env = std::getenv("FEWBIT_B200_SKETCH_BN")) only_bn = std::atoi(env);   // tuning runs
-    if (const char *env = std::getenv("FEWBIT_B200_SKETCH_SPLITK")) only_sk = std::atoi(env);
+    pl.bn = 64, pl.split_k = 1;
+    const int only_bn = env_int("FEWBIT_B200_SKETCH_BN", 0), only_sk = env_int("FEWBIT_B200_SKETCH_SPLITK", 0);   // tuning runs
     for (int cand = 160; cand >= 64; cand -= 16) {
-        if ((cand / 8) % cy != 0) continue;
+        if ((cand / 8) % pl.cy != 0) continue;
         if (only_bn && cand != only_bn) continue;
-        const int ptiles = ((rows + cand - 1) / cand + cx - 1) / cx * cx;
+        const int ptiles = (rows + cand - 1) / cand;
         for (int sk = 1; sk <= 8 && sk <= kblocks; ++sk) {
             if (only_sk && sk != only_sk) continue;
             const int64_t ctas = (int64_t)ptiles * dtiles * sk;
@@ -758,14 +786,26 @@ static void plan(int rows, int features, int64_t tokens, int kind, int sms, int 
             // under ~1300 (pipeline round trip; 12 MMAs of ~90-107 cycles).  Per CTA: ~20000 for
             // prologue + epilogue (the epilogue writes at HBM speed).  Split-K adds the partials'
             // round trip through memory: 8 bytes per output element and split at ~5 TB/s.
-            const double generated = kind == 0 ? (double)cand / cy * 17.0 : 0.0;
+            const double generated = kind == 0 ? (double)cand / pl.cy * 17.0 : 0.0;
             const double block = std::max({generated, 1300.0, cand * 9.0});   // 12 MMAs: ~9 cycles per row
             const double per_cta = (double)((kblocks + sk - 1) / sk) * block + 20000.0;
             const double reduce = sk > 1 ? (double)sk * rows * features * 8.0 / 5e12 * 1.9e9 : 0.0;
             const double cost = (double)waves * per_cta + reduce;
-            if (cost < best) best = cost, bn = cand, split_k = sk;
+            if (cost < best) best = cost, pl.bn = cand, pl.split_k = sk;
         }
     }
+    int per = (int)((kblocks + pl.split_k - 1) / pl.split_k);
+    pl.kblocks_per_split = per + (per & 1);
+    // Shared memory: the S ring first (each CTA stores only the rows it generates in pair mode, the
+    // whole BN-row slot otherwise), the X ring gets what is left.
+    const int tile_rows = ((pl.pair ? pl.bn / 2 : pl.bn) + 7) / 8 * 8;
+    pl.s_tile_bytes = tile_rows * 128;
+    pl.s_slots = std::min(kMaxSlots, std::max(1, env_int("FEWBIT_B200_SKETCH_SLOTS", pl.pair ? 3 : 2)));
+    const int room = kSmemLimit - 1024 /* alignment */ - kBarrierBytes - pl.s_slots * 2 * pl.s_tile_bytes;
+    pl.x_units = std::min(kMaxUnits, room / kUnitBytes);
+    if (const int v = env_int("FEWBIT_B200_SKETCH_UNITS", 0)) pl.x_units = std::min(pl.x_units, std::max(v, 1));
+    pl.smem_bytes = pl.x_units * kUnitBytes + pl.s_slots * 2 * pl.s_tile_bytes + kBarrierBytes + 1024;
+    return pl;
 }
 
 }  // namespace sketch
@@ -777,12 +817,12 @@ using namespace fewbit::sketch;
 extern "C" {
 
 size_t fewbit_sketch_workspace_bytes(int64_t tokens, int features, int rows) {
-    int bn, split_k, cx, cy;
-    bool pair;
-    plan(rows, features, tokens, 0, sm_count(), bn, split_k, cx, cy, pair);
-    size_t bytes = split_k > 1 ? (size_t)split_k * rows * features * sizeof(float) : 0;
-    plan(rows, features, tokens, 1, sm_count(), bn, split_k, cx, cy, pair);   // the larger of the two kinds
-    return std::max(bytes, split_k > 1 ? (size_t)split_k * rows * features * sizeof(float) : (size_t)0);
+    size_t bytes = 0;
+    for (int kind = 0; kind < 2; ++kind) {      // the larger of the two kinds
+        const Plan pl = plan(rows, features, tokens, kind, sm_count());
+        if (pl.split_k > 1) bytes = std::max(bytes, (size_t)pl.split_k * rows * features * sizeof(float));
+    }
+    return bytes;
 }
 
 int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t tokens, int features,
@@ -793,10 +833,11 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
     EncodeTiled encode = encode_tiled();
     if (!encode) return (int)cudaErrorNotSupported;
     cudaStream_t s = (cudaStream_t)stream;
-    int bn, split_k, cx, cy;
-    bool pair;
-    plan(rows, features, tokens, kind, sm_count(), bn, split_k, cx, cy, pair);
+    const Plan pl = plan(rows, features, tokens, kind, sm_count());
+    const int bn = pl.bn, split_k = pl.split_k, cy = pl.cy;
+    const bool pair = pl.pair;
     if (split_k > 1 && !workspace) return FEWBIT_EINVAL;
+    if (pl.x_units < 3) return (int)cudaErrorInvalidConfiguration;
 
     CUtensorMap map;
     const cuuint64_t dims[2] = {(cuuint64_t)features, (cuuint64_t)std::max<int64_t>(tokens, 1)};
@@ -807,15 +848,15 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return (int)cudaErrorInvalidValue;
 
-    const int64_t kblocks = (tokens + kBlockK - 1) / kBlockK;
     Params prm;
     prm.out = split_k > 1 ? static_cast<float *>(workspace) : out;
     prm.tokens = tokens, prm.features = features, prm.rows = rows, prm.block_rows = bn;
-    prm.kblocks_per_split = (int)((kblocks + split_k - 1) / split_k);
-    prm.split_k = split_k, prm.scale = scale, prm.kind = kind, prm.cluster_x = cx, prm.cluster_y = cy;
-    prm.debug = 0;
+    prm.kblocks_per_split = pl.kblocks_per_split;
+    prm.split_k = split_k, prm.scale = scale, prm.kind = kind, prm.cluster_y = cy;
+    prm.x_units = pl.x_units, prm.s_slots = pl.s_slots, prm.s_tile_bytes = pl.s_tile_bytes;
+    prm.prefetch = env_int("FEWBIT_B200_SKETCH_PREFETCH", 0);
+    prm.debug = env_int("FEWBIT_B200_SKETCH_DEBUG", 0);
     prm.trace = nullptr;
-    if (const char *env = std::getenv("FEWBIT_B200_SKETCH_DEBUG")) prm.debug = std::atoi(env);
     static unsigned long long *trace_buffer = nullptr;
     const bool tracing = std::getenv("FEWBIT_B200_SKETCH_TRACE") != nullptr;
     if (tracing) {
@@ -831,22 +872,21 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
     int device = 0;
     if (cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= 64) device = 0;
     if (!configured[device]) {
-        cudaError_t e = cudaFuncSetAttribute(sketch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(sketch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(sketch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        e = cudaFuncSetAttribute(sketch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e != cudaSuccess) return (int)e;
         configured[device] = true;
     }
     cudaLaunchConfig_t cfg{};
-    // grid.x rounded up to whole clusters: surplus CTAs compute rows >= P, which are never stored
-    cfg.gridDim = dim3(((rows + bn - 1) / bn + cx - 1) / cx * cx, (features + kFeaturesPerCta - 1) / kFeaturesPerCta, split_k);
+    cfg.gridDim = dim3((rows + bn - 1) / bn, (features + kFeaturesPerCta - 1) / kFeaturesPerCta, split_k);
     if (pair) std::swap(cfg.gridDim.x, cfg.gridDim.y);      // feature tiles (the pairs) along x
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.dynamicSmemBytes = pl.smem_bytes;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = pair ? 2 : cx, attr[0].val.clusterDim.y = pair ? 1 : cy, attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = pair ? 2 : 1, attr[0].val.clusterDim.y = pair ? 1 : cy, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
     cudaError_t launched = pair ? cudaLaunchKernelEx(&cfg, sketch_kernel<true>, map, prm)
                                 : cudaLaunchKernelEx(&cfg, sketch_kernel<false>, map, prm);
@@ -857,11 +897,11 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
         cudaStreamSynchronize(s);
         cudaMemcpy(t, trace_buffer, sizeof(t), cudaMemcpyDeviceToHost);
         std::fprintf(stderr,
-                     "[sketch trace] D=%d bn=%d split_k=%d pair=%d grid=%ux%ux%u | setup %.1f us, first MMA +%.1f, "
+                     "[sketch trace] D=%d bn=%d split_k=%d pair=%d units=%d slots=%d grid=%ux%ux%u | setup %.1f us, first MMA +%.1f, "
                      "MMA loop %.1f (waited X %.1f, S %.1f), generators done +%.1f (waited empty %.1f, generating %.1f), "
-                     "accumulators seen +%.1f, epilogue %.1f | generator thread 0, cycles per stage: generate %llu, proxy fence %llu, "
+                     "accumulators seen +%.1f, epilogue %.1f | generator thread 0, cycles per 128-token slot: generate %llu, proxy fence %llu, "
                      "sync+push %llu, arrive %llu\n",
-                     features, bn, split_k, (int)pair, cfg.gridDim.x, cfg.gridDim.y, cfg.gridDim.z,
+                     features, bn, split_k, (int)pair, pl.x_units, pl.s_slots, cfg.gridDim.x, cfg.gridDim.y, cfg.gridDim.z,
                      (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3, t[6] * 1e-3, t[7] * 1e-3,
                      (t[9] - t[1]) * 1e-3, t[8] * 1e-3, t[10] * 1e-3, (t[4] - t[1]) * 1e-3, (t[5] - t[4]) * 1e-3, t[11], t[12], t[13], t[14]);
     }
