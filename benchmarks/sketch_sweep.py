@@ -14,7 +14,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from fewbit_b200 import native  # noqa: E402
 
 PREFIX = 'FEWBIT_B200_SKETCH_'
-tokens, rows = 16384, 3276
+tokens, rows = 16384, int(os.environ.get('SWEEP_ROWS', '3276'))
 dev = 'cuda:0'
 shapes = [int(v) for v in os.environ.get('SWEEP_FEATURES', '768,3072').split(',')]
 xs = {d: torch.randn(tokens, d, device=dev).to(torch.bfloat16) for d in shapes}

@@ -25,34 +25,44 @@
 // sketch row the 32 lanes of a warp hold 32 consecutive features.
 //
 // CTA = 16 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-15
-// generate S; all 16 warps run the epilogue (tcgen05.ld -> scale -> global).  Three-stage
-// mbarrier pipeline: full_x (TMA bytes), full_s (generator warps), empty (tcgen05.commit).
+// generate S; all 16 warps run the epilogue (tcgen05.ld -> scale -> global).  Two rings in shared
+// memory, each with full/empty mbarriers (TMA bytes or generator warps / tcgen05.commit):
+//   X ring: three stages of 64 tokens x 384 features (48 KB each);
+//   S ring: slots of 128 tokens (two 64-token K-major tiles), as many as fit beside the X ring
+//           (4 in pair mode, 2 otherwise).  The generators run up to that many slots ahead of the
+//           MMAs, so neither their latency nor the hand-over of a slot between the CTAs of a pair
+//           sits on the round trip of an X stage (profiles/r02_sketch_trace.md: with one ring the
+//           MMA warp waited for S 60 % of the time while the generators were busy 75 % of it).
+// Gaussian S: a generator thread owns the same (row, 16-byte chunk) positions of every slot and makes
+// the Philox calls of the NEXT slot in the same straight-line block as the Box-Muller evaluations
+// of this one, dealt out between the Philox rounds: multiply-xor rounds (ALU / FMA pipes) and
+// lg2 / sqrt / sin / cos chains (XU pipe) overlap instead of taking turns.
 // The TMA and MMA loops are walked by their whole warp with only the asynchronous instruction under
 // an elect.sync predicate: under `if (lane == 0)` the compiler wraps every UTCHMMA in a uniform-
 // register retry loop that costs ~150 cycles per MMA, twice the MMA itself (measured).
 // Grid = (ceil(P / BN), ceil(D / 384), split_k); split-K partials are reduced by a tiny kernel.
 //
-// Three ways for CTAs that need the same data to share it (chosen by plan()):
-//  * pair mode, the default for Gaussian S when D is a multiple of 768: a 2 x 1 cluster is a CTA
-//    pair in the tcgen05 sense (cta_group::2).  The two CTAs own the two 384-feature halves of a
-//    768-feature slab and generate HALF of every S tile each; one M = 256 MMA, issued by the
-//    leader, reads X^T from both shared memories and each half of S once for both.  S is thus
-//    generated once per slab instead of once per feature tile, nothing is copied, and the MMA's
-//    shared-memory traffic per SM drops by a third.  The leader's full_x counts the TMA bytes of
-//    both CTAs (the peer's TMA signals the leader's barrier, .cta_group::2 form); the peer's
-//    generators arrive on a local barrier and its idle warp 1 forwards that to the leader with a
-//    cluster-scope release (~0.5 us, off the generators' critical path).  Grid axes are swapped
-//    (feature tiles along x): the hardware pairs CTAs that are adjacent along x of the cluster.
-//  * along y (feature tiles) without cta_group::2, cluster (1, 2): CTA ry generates rows
-//    [ry BN/2, (ry+1) BN/2) of each stage into its own shared memory and pushes that block to
-//    its y-peer with cp.async.bulk.shared::cluster (async proxy; completes transaction bytes on
-//    the PEER's full_s barrier, so the tensor core sees the data without a generic-proxy
-//    hand-over).  Used for Rademacher S at D = 768: that case is bound by the MMA pipeline, and
-//    the pair's extra signalling hop costs more than the halved S traffic saves.
-//  * along x (sketch-row tiles), cluster (2, 1) with TMA multicast of the X boxes: kept for A/B
-//    runs (FEWBIT_B200_SKETCH_CLUSTER), measured slower -- L2 is not the limiter.
-// A stage may be overwritten only when every CTA of the cluster has consumed it: tcgen05.commit
-// multicasts its arrival to the `empty` barrier of all CTAs of the cluster.
+// Two ways for CTAs that need the same S to share it (chosen by plan()):
+//  * pair mode, whenever D is a multiple of 768: a 2 x 1 cluster is a CTA pair in the tcgen05 sense
+//    (cta_group::2).  The two CTAs own the two 384-feature halves of a 768-feature slab and generate
+//    HALF of every S slot each; one M = 256 MMA, issued by the leader, reads X^T from both shared
+//    memories and each half of S once for both.  S is thus generated once per slab instead of once
+//    per feature tile, nothing is copied, and the MMA's shared-memory traffic per SM drops by a
+//    third.  The leader's full_x counts the TMA bytes of both CTAs (the peer's TMA signals the
+//    leader's barrier, .cta_group::2 form); the peer's generators arrive on a local barrier and its
+//    idle warp 1 forwards that to the leader with a cluster-scope release (~0.5 us, off the
+//    generators' critical path).  Grid axes are swapped (feature tiles along x): the hardware pairs
+//    CTAs that are adjacent along x of the cluster.
+//  * along y (two feature tiles that are not a full pair) without cta_group::2, cluster (1, 2): CTA
+//    ry generates rows [ry BN/2, (ry+1) BN/2) of each slot into its own shared memory and pushes
+//    that block to its y-peer with cp.async.bulk.shared::cluster (async proxy; completes transaction
+//    bytes on the PEER's full_s barrier, so the tensor core sees the data without a generic-proxy
+//    hand-over).
+// Tried and dropped (profiles/r01_sketch_kernel.md, r02_sketch_unit_ring.txt): sharing X between row
+// tiles by TMA multicast, clusters of 8 along y, an X ring in 16 KB units with one commit each, L2
+// prefetch ahead of the TMA, the leader loading the peer's X boxes, more generator warps.
+// A stage or slot may be overwritten only when every CTA of the cluster has consumed it:
+// tcgen05.commit multicasts its arrival to the `empty` barriers of all CTAs of the cluster.
 // FEWBIT_B200_SKETCH_TRACE=1 prints one CTA's timeline per call (benchmarks/sketch_trace.py).
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -62,6 +72,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "../../include/fewbit_b200.h"
 
@@ -80,8 +91,9 @@ constexpr int kBlockK = 64;            // tokens per stage (four K = 16 MMAs per
 constexpr int kFeaturesPerCta = 384;   // 3 MMA M-blocks of 128
 constexpr int kMaxRows = 160;          // BN: sketch rows per CTA (TMEM: 3 * 160 <= 512 columns)
 constexpr int kBoxBytes = 64 * 64 * 2;                        // one TMA box: 64 tokens x 64 features
-constexpr int kUnitBytes = 2 * kBoxBytes;                     // X ring entry: 64 tokens x 128 features
-constexpr int kMaxUnits = 12, kMaxSlots = 4;                  // ring sizes are chosen at launch (shared memory)
+constexpr int kStages = 3;                                    // X ring: stages of 64 tokens x 384 features
+constexpr int kXStageBytes = (kFeaturesPerCta / 64) * kBoxBytes;   // 49152
+constexpr int kMaxSlots = 4;                                  // S ring: slots of 128 tokens, count chosen at launch
 constexpr int kBarrierBytes = 512;
 constexpr int kSmemLimit = 232448;                            // 227 KB per CTA
 constexpr int kGeneratorWarps = kThreads / 32 - 2;
@@ -122,10 +134,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
         "l"(map), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1) {   // into L2 only
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1)
-                 : "memory");
 }
 // kPair selects the two-SM forms (cta_group::2): one MMA spans the CTA pair of a cluster, M = 256.
 template <bool kPair>
@@ -170,10 +178,10 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
             : "memory");
     } while (!done);
 }
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {   // arrives on both CTAs of the pair
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-        "h"((uint16_t)3)
+        "h"(mask)
         : "memory");
 }
 // One lane of a converged warp.  The TMA and MMA loops are run by their WHOLE warp with only the
@@ -197,6 +205,11 @@ __device__ __forceinline__ uint32_t cluster_cta_x() {
 __device__ __forceinline__ uint32_t cluster_cta_y() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctaid.y;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
 __device__ __forceinline__ void cluster_sync() {
@@ -233,8 +246,16 @@ __device__ __forceinline__ void tmem_load16(uint32_t taddr, uint32_t (&v)[16]) {
           "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
           "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// The registers of an asynchronous TMEM read hold data only after the wait: passing them through
+// the wait (and a second, empty statement ordered after it) keeps the compiler from using them early.
+#define FEWBIT_SIXTEEN(v) "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), \
+                          "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+__device__ __forceinline__ void tmem_load_wait(uint32_t (&v)[16], uint32_t (&w)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : FEWBIT_SIXTEEN(v)::"memory");
+    asm volatile("" : FEWBIT_SIXTEEN(w)::"memory");
+}
+#undef FEWBIT_SIXTEEN
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100): start address, leading
 // and stride byte offsets in 16-byte units, version 1, layout SWIZZLE_128B = 2.
@@ -301,26 +322,59 @@ __device__ __forceinline__ uint4 normal_octet(const Philox &rng, uint32_t o, uin
     const uint4 r = rng(make_uint4(o, p, off_lo, off_hi));
     return make_uint4(normal_pair(r.x), normal_pair(r.y), normal_pair(r.z), normal_pair(r.w));
 }
-// Two octets at once: the two Philox chains and the eight Box-Muller evaluations are independent,
-// and written as one straight-line block the scheduler interleaves them (a generator thread is
-// otherwise latency-bound: ~10 dependent multiply-xor rounds, then lg2 -> sqrt).
-__device__ __forceinline__ void normal_octet2(const Philox &rng, uint32_t o0, uint32_t p0, uint32_t o1, uint32_t p1,
-                                              uint32_t off_lo, uint32_t off_hi, uint4 &v0, uint4 &v1) {
-    uint4 c0 = make_uint4(o0, p0, off_lo, off_hi), c1 = make_uint4(o1, p1, off_lo, off_hi);
+// N octets at once: the Philox chains and the Box-Muller evaluations are independent, and written
+// as one straight-line block the scheduler interleaves them.
+template <int N>
+__device__ __forceinline__ void normal_octets(const Philox &rng, const uint32_t (&o)[N], const uint32_t (&p)[N],
+                                              uint32_t off_lo, uint32_t off_hi, uint4 (&v)[N]) {
+    uint4 c[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) c[q] = make_uint4(o[q], p[q], off_lo, off_hi);
     uint32_t a = rng.k0, b = rng.k1;
 #pragma unroll
     for (int round = 0; round < kPhiloxRounds; ++round) {
-        const uint32_t h00 = __umulhi(0xD2511F53u, c0.x), l00 = 0xD2511F53u * c0.x;
-        const uint32_t h10 = __umulhi(0xD2511F53u, c1.x), l10 = 0xD2511F53u * c1.x;
-        const uint32_t h01 = __umulhi(0xCD9E8D57u, c0.z), l01 = 0xCD9E8D57u * c0.z;
-        const uint32_t h11 = __umulhi(0xCD9E8D57u, c1.z), l11 = 0xCD9E8D57u * c1.z;
-        c0 = make_uint4(h01 ^ c0.y ^ a, l01, h00 ^ c0.w ^ b, l00);
-        c1 = make_uint4(h11 ^ c1.y ^ a, l11, h10 ^ c1.w ^ b, l10);
+#pragma unroll
+        for (int q = 0; q < N; ++q) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c[q].x), lo0 = 0xD2511F53u * c[q].x;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[q].z), lo1 = 0xCD9E8D57u * c[q].z;
+            c[q] = make_uint4(hi1 ^ c[q].y ^ a, lo1, hi0 ^ c[q].w ^ b, lo0);
+        }
         a += 0x9E3779B9u;
         b += 0xBB67AE85u;
     }
-    v0 = make_uint4(normal_pair(c0.x), normal_pair(c0.y), normal_pair(c0.z), normal_pair(c0.w));
-    v1 = make_uint4(normal_pair(c1.x), normal_pair(c1.y), normal_pair(c1.z), normal_pair(c1.w));
+#pragma unroll
+    for (int q = 0; q < N; ++q)
+        v[q] = make_uint4(normal_pair(c[q].x), normal_pair(c[q].y), normal_pair(c[q].z), normal_pair(c[q].w));
+}
+// The same with the two halves taken from different slots: turns the counters `next` into Philox
+// outputs (for the following slot) while `ready`, the outputs made one slot earlier, become normals.
+template <int N>
+__device__ __forceinline__ void philox_and_normals(const Philox &rng, uint4 (&next)[N], const uint4 (&ready)[N],
+                                                   uint4 (&v)[N], uint32_t zero) {
+    uint32_t a = rng.k0, b = rng.k1;
+    uint32_t in[4 * N], out[4 * N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) in[4 * q] = ready[q].x, in[4 * q + 1] = ready[q].y, in[4 * q + 2] = ready[q].z, in[4 * q + 3] = ready[q].w;
+    // The Box-Muller pairs are dealt out between the Philox rounds.  ptxas would hoist all MUFU chains to
+    // the top of the block (ALU idle, then XU idle); `zero` -- a kernel parameter that is 0 -- makes the
+    // input of a pair nominally depend on the round before it, at one LOP3 per pair.
+#pragma unroll
+    for (int round = 0; round < kPhiloxRounds; ++round) {
+#pragma unroll
+        for (int q = 0; q < N; ++q) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, next[q].x), lo0 = 0xD2511F53u * next[q].x;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, next[q].z), lo1 = 0xCD9E8D57u * next[q].z;
+            next[q] = make_uint4(hi1 ^ next[q].y ^ a, lo1, hi0 ^ next[q].w ^ b, lo0);
+        }
+        a += 0x9E3779B9u;
+        b += 0xBB67AE85u;
+#pragma unroll
+        for (int i = 0; i < 4 * N; ++i)
+            if (i >= 4 * N * round / kPhiloxRounds && i < 4 * N * (round + 1) / kPhiloxRounds)
+                out[i] = normal_pair(in[i] ^ (next[i % N].x & zero));
+    }
+#pragma unroll
+    for (int q = 0; q < N; ++q) v[q] = make_uint4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
 }
 // kind 1: 128 signs S[p][128c .. 128c+127]; bit b of word w is entry 32w + b.
 __device__ __forceinline__ uint4 sign_block(const Philox &rng, uint32_t c, uint32_t p, uint32_t off_lo,
@@ -351,14 +405,12 @@ struct Params {
     float scale;         // applied here only when split_k == 1
     uint32_t seed_lo, seed_hi, off_lo, off_hi;
     int kind;
+    uint32_t zero;       // 0, opaque to the compiler (see philox_and_normals)
     int cluster_y;       // CTAs along grid.y that share one generated S slot
-    int x_units;         // X ring: entries of 64 tokens x 128 features
     int s_slots;         // S ring: entries of 128 tokens x (my share of) BN rows
     int s_tile_bytes;    // one 64-token half of an S slot
-    int prefetch;        // stages ahead that the TMA warp pulls X into L2 (0 = off)
     unsigned long long *trace;   // FEWBIT_B200_SKETCH_TRACE: per-role time stamps of CTA (0,0,0), else null
-    int debug;           // timing experiments only (results are garbage): 1 = skip generating S,
-                         // 4 = skip issuing MMAs
+    int debug;           // timing experiments only (results are garbage): 1 = skip generating S, 4 = skip issuing MMAs
 };
 
 template <bool kPair>
@@ -367,11 +419,11 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzled tiles need 1024-byte alignment.
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int units = prm.x_units, slots = prm.s_slots;
+    const int slots = prm.s_slots;
     const uint32_t tile_bytes = (uint32_t)prm.s_tile_bytes;          // one 64-token half of an S slot
-    uint8_t *s_ring = smem + units * kUnitBytes;
+    uint8_t *s_ring = smem + kStages * kXStageBytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_ring + slots * 2 * tile_bytes);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kMaxUnits + 2 * kMaxSlots + 1);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 2 * kMaxSlots + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool traced = prm.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
@@ -380,18 +432,18 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     const int p0 = (kPair ? blockIdx.y : blockIdx.x) * prm.block_rows;
     const int d0 = (kPair ? blockIdx.x : blockIdx.y) * kFeaturesPerCta;
     const int bn = prm.block_rows;
-    const int nblocks = min(3, (prm.features - d0 + 127) / 128);   // 128-feature MMA blocks = X units per stage
+    const int nblocks = min(3, (prm.features - d0 + 127) / 128);   // 128-feature MMA blocks
     const int nboxes = min(6, (prm.features - d0 + 63) / 64);
     const int64_t total_kb = (prm.tokens + kBlockK - 1) / kBlockK;
-    const int64_t kb_begin = (int64_t)blockIdx.z * prm.kblocks_per_split;      // even: S slots span two k-blocks
+    const int64_t kb_begin = (int64_t)blockIdx.z * prm.kblocks_per_split;      // even: S slots span two stages
     const int64_t kb_end = min(total_kb, kb_begin + prm.kblocks_per_split);
     const int iters = (int)max((int64_t)0, kb_end - kb_begin);
 
-    auto full_x = [&](int u) { return smem_addr(bars + u); };
-    auto empty_x = [&](int u) { return smem_addr(bars + kMaxUnits + u); };
-    auto full_s = [&](int j) { return smem_addr(bars + 2 * kMaxUnits + j); };
-    auto empty_s = [&](int j) { return smem_addr(bars + 2 * kMaxUnits + kMaxSlots + j); };
-    const uint32_t accum_full = smem_addr(bars + 2 * kMaxUnits + 2 * kMaxSlots);
+    auto full_x = [&](int s) { return smem_addr(bars + s); };
+    auto empty_x = [&](int s) { return smem_addr(bars + kStages + s); };
+    auto full_s = [&](int j) { return smem_addr(bars + 2 * kStages + j); };
+    auto empty_s = [&](int j) { return smem_addr(bars + 2 * kStages + kMaxSlots + j); };
+    const uint32_t accum_full = smem_addr(bars + 2 * kStages + 2 * kMaxSlots);
     const uint32_t x_ring = smem_addr(smem);
 
     const int cy = prm.cluster_y;                            // CTAs that share one generated S slot
@@ -403,10 +455,14 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     // reads X^T from both shared memories and each half of S once for both.  The leader's full_x
     // counts the TMA bytes of both CTAs, its full_s the generator warps of both.
     const bool leader = !kPair || ry == 0;
+    // the CTAs that share S are ranks [group0, group0 + Cy) of the cluster (group0 = 0 today; kept
+    // general so that the cluster may grow along another axis)
+    const uint32_t group0 = cluster_cta_rank() - ry;
+    const uint16_t group_mask = (uint16_t)(((1u << (kPair ? 2 : cy)) - 1u) << group0);
     if (threadIdx.x == 0) {
-        for (int u = 0; u < units; ++u) {
-            mbar_init(full_x(u), 1);
-            mbar_init(empty_x(u), kPair ? 1 : cy);                      // one commit per issuing CTA
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_x(s), 1);
+            mbar_init(empty_x(s), kPair ? 1 : cy);                      // one commit per issuing CTA
         }
         for (int j = 0; j < slots; ++j) {
             // own generator warps, + the peer's forwarded arrival (pair leader) or the expect_tx arrival (pushing)
@@ -431,41 +487,33 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (kPair || cy > 1) cluster_sync();      // peers' barriers exist before anyone signals them
+    const bool clustered = kPair || cy > 1;
+    if (clustered) cluster_sync();            // peers' barriers exist before anyone signals them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     if (traced && threadIdx.x == 0) prm.trace[1] = now_ns();
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer ----
-        // One ring entry ("unit") = the two 64-feature boxes of one MMA block: 16 KB.  A stage (64 tokens)
-        // takes `nblocks` consecutive units; each is released by its own commit, so the ring refills
-        // at a third of a stage's granularity and need not hold a whole number of stages.
-        int u = 0;
-        uint32_t phase = 0;
-        for (int it = 0; it < iters; ++it) {
-            const int token = (int)((kb_begin + it) * kBlockK);
-            if (prm.prefetch > 0 && it + prm.prefetch < iters && elect_one())
-                for (int b = 0; b < nboxes; ++b)
-                    tma_prefetch_2d(&x_map, d0 + 64 * b, token + prm.prefetch * kBlockK);
-            for (int m = 0; m < nblocks; ++m) {
-                mbar_wait(empty_x(u), phase ^ 1);
+        {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % kStages;
+                mbar_wait(empty_x(s), ((it / kStages) & 1) ^ 1);
+                const int token = (int)((kb_begin + it) * kBlockK);
                 if (elect_one()) {
-                    const int boxes = min(2, nboxes - 2 * m);
-                    const uint32_t dst = x_ring + u * kUnitBytes;
+                    const uint32_t dst = x_ring + s * kXStageBytes;
                     if constexpr (kPair) {
-                        if (leader) mbar_expect_tx(full_x(u), 2 * boxes * kBoxBytes);     // both CTAs' boxes
-                        const uint32_t bar = map_to_cta(full_x(u), 0);
-                        for (int b = 0; b < boxes; ++b)
-                            tma_load_2d_pair(dst + b * kBoxBytes, &x_map, d0 + 128 * m + 64 * b, token, bar);
+                        if (leader) mbar_expect_tx(full_x(s), 2 * nboxes * kBoxBytes);     // both CTAs' boxes
+                        const uint32_t bar = map_to_cta(full_x(s), group0);                 // counted on the leader's barrier
+                        for (int b = 0; b < nboxes; ++b)
+                            tma_load_2d_pair(dst + b * kBoxBytes, &x_map, d0 + 64 * b, token, bar);
                     } else {
-                        mbar_expect_tx(full_x(u), boxes * kBoxBytes);
-                        for (int b = 0; b < boxes; ++b)
-                            tma_load_2d(dst + b * kBoxBytes, &x_map, d0 + 128 * m + 64 * b, token, full_x(u));
+                        mbar_expect_tx(full_x(s), nboxes * kBoxBytes);
+                        for (int b = 0; b < nboxes; ++b)
+                            tma_load_2d(dst + b * kBoxBytes, &x_map, d0 + 64 * b, token, full_x(s));
                     }
                 }
                 __syncwarp();
-                if (++u == units) u = 0, phase ^= 1;
             }
         }
     } else if (warp == 1) {
@@ -477,7 +525,7 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
                                    ((uint32_t)(bn >> 3) << 17) | (((kPair ? 256u : 128u) >> 4) << 24);
             // Shared-memory descriptors differ only in the 14-bit address field of their low word:
             //   A: 64-feature groups 8192 B apart (LBO), 8-token groups 1024 B apart (SBO); +2048 B per
-            //      16 tokens; one unit = 128 features.
+            //      16 tokens; 128 features = two boxes.
             //   B: rows of 128 B (64 tokens), 8-row groups 1024 B apart (SBO); +32 B per 16 tokens.
             const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
             const uint32_t a_lo = ((x_ring & 0x3FFFFu) >> 4) | ((uint32_t)(kBoxBytes >> 4) << 16);
@@ -485,56 +533,59 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
             const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base, 0);
             const bool skip_mma = (prm.debug & 4) != 0;
             unsigned long long wait_x = 0, wait_s = 0;
-            int u = 0, j = 0;
-            uint32_t phase = 0, sphase = 0;
+            int j = 0;
+            uint32_t sphase = 0;
             for (int it = 0; it < iters; ++it) {
-                const int half = it & 1;
+                const int s = it % kStages, half = it & 1;
+                const unsigned long long w0 = traced ? now_ns() : 0;
                 if (half == 0) {
-                    const unsigned long long w0 = traced ? now_ns() : 0;
                     if constexpr (kPair) mbar_wait_cluster(full_s(j), sphase);   // the peer's generators wrote its half
                     else mbar_wait(full_s(j), sphase);
-                    if (traced && lane == 0) wait_s += now_ns() - w0;
                 }
-                const uint32_t b_tile = b_lo + (uint32_t)(((uint32_t)(2 * j + half) * tile_bytes) >> 4);
-                for (int m = 0; m < nblocks; ++m) {
-                    const unsigned long long w0 = traced ? now_ns() : 0;
-                    mbar_wait(full_x(u), phase);
-                    if (traced && lane == 0) {
-                        const unsigned long long w1 = now_ns();
-                        wait_x += w1 - w0;
-                        if (it == 0 && m == 0) prm.trace[2] = w1;
-                    }
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (elect_one()) {
-                        if (!skip_mma) {
-                            const uint32_t a_unit = a_lo + (uint32_t)u * (uint32_t)(kUnitBytes >> 4);
+                const unsigned long long w1 = traced ? now_ns() : 0;
+                mbar_wait(full_x(s), (it / kStages) & 1);
+                if (traced && lane == 0) {
+                    const unsigned long long w2 = now_ns();
+                    wait_s += w1 - w0, wait_x += w2 - w1;
+                    if (it == 0) prm.trace[2] = w2;
+                }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const bool slot_done = half == 1 || it == iters - 1;      // both halves of the S slot consumed
+                if (elect_one()) {
+                    if (!skip_mma) {
+                        const uint32_t a_stage = a_lo + (uint32_t)s * (uint32_t)(kXStageBytes >> 4);
+                        const uint32_t b_tile = b_lo + (uint32_t)(((uint32_t)(2 * j + half) * tile_bytes) >> 4);
 #pragma unroll
-                            for (int k = 0; k < kBlockK / 16; ++k) {
-                                const uint64_t desc_a = ((uint64_t)desc_hi << 32) | (a_unit + (uint32_t)((2048 * k) >> 4));
-                                const uint64_t desc_b = ((uint64_t)desc_hi << 32) | (b_tile + 2u * k);
-                                umma_bf16<kPair>(tmem + m * kMaxRows, desc_a, desc_b, idesc, (it | k) != 0);
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            const uint64_t desc_b = ((uint64_t)desc_hi << 32) | (b_tile + 2u * k);
+#pragma unroll
+                            for (int m = 0; m < 3; ++m) {
+                                if (m < nblocks) {
+                                    const uint64_t desc_a = ((uint64_t)desc_hi << 32) |
+                                                            (a_stage + (uint32_t)((m * 2 * kBoxBytes + 2048 * k) >> 4));
+                                    umma_bf16<kPair>(tmem + m * kMaxRows, desc_a, desc_b, idesc, (it | k) != 0);
+                                }
                             }
                         }
-                        // the unit is reusable once these MMAs have read it -- in every CTA of the cluster
-                        if constexpr (kPair) umma_commit_pair(empty_x(u));
-                        else if (cy > 1) umma_commit_cluster(empty_x(u), (uint16_t)((1u << cy) - 1));
-                        else umma_commit(empty_x(u));
                     }
-                    __syncwarp();
-                    if (++u == units) u = 0, phase ^= 1;
-                }
-                if (half == 1 || it == iters - 1) {       // both halves of the S slot consumed
-                    if (elect_one()) {
-                        if constexpr (kPair) umma_commit_pair(empty_s(j));
-                        else if (cy > 1) umma_commit_cluster(empty_s(j), (uint16_t)((1u << cy) - 1));
-                        else umma_commit(empty_s(j));
+                    // The X stage is reusable once these MMAs have read it -- in every CTA of the cluster;
+                    // the S slot once both of its halves have been.
+                    if constexpr (kPair) {
+                        umma_commit_pair(empty_x(s), group_mask);
+                        if (slot_done) umma_commit_pair(empty_s(j), group_mask);
+                    } else if (cy > 1) {
+                        umma_commit_cluster(empty_x(s), group_mask);
+                        if (slot_done) umma_commit_cluster(empty_s(j), group_mask);
+                    } else {
+                        umma_commit(empty_x(s));
+                        if (slot_done) umma_commit(empty_s(j));
                     }
-                    __syncwarp();
-                    if (++j == slots) j = 0, sphase ^= 1;
                 }
+                __syncwarp();
+                if (slot_done && ++j == slots) j = 0, sphase ^= 1;
             }
             if (elect_one()) {   // accumulators complete (in both CTAs of a pair)
-                if constexpr (kPair) umma_commit_pair(accum_full);
+                if constexpr (kPair) umma_commit_pair(accum_full, group_mask);
                 else umma_commit(accum_full);
             }
             __syncwarp();
@@ -547,7 +598,7 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
             uint32_t sphase = 0;
             for (int n = 0; n < (iters + 1) / 2; ++n) {
                 mbar_wait(full_s(j), sphase);
-                if (elect_one()) mbar_arrive_cluster(map_to_cta(full_s(j), 0));
+                if (elect_one()) mbar_arrive_cluster(map_to_cta(full_s(j), group0));
                 __syncwarp();
                 if (++j == slots) j = 0, sphase ^= 1;
             }
@@ -562,43 +613,125 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
         long long ph[4] = {0, 0, 0, 0};      // cycles: generate + store, proxy fence, block sync + push, arrive
         const int row0 = (int)ry * my_rows;                // this CTA's block of the slot
         const int place = kPair ? 0 : row0;                // pair mode: the block sits at the tile start
-        int j = 0;
-        uint32_t sphase = 0;
+        // Gaussian: one Philox call = 8 normals = one 16-byte chunk, 16 chunks per row and slot.  The
+        // chunks are dealt evenly: `per` to each of the first `active` threads, taken in groups of up to
+        // four whose Philox chains and Box-Muller evaluations interleave (a single chain is latency-
+        // bound: ~10 dependent multiply-xor rounds, then lg2 -> sqrt).
+        const int chunks = my_rows * 16;
+        const int per = (chunks + kGeneratorThreads - 1) / kGeneratorThreads;
+        const int active = (chunks + per - 1) / per;
+        const int groups = (per + 3) / 4, group = (per + groups - 1) / groups;
         const int nslots = (iters + 1) / 2;
-        for (int n = 0; n < nslots; ++n) {
-            const unsigned long long w0 = traced && gt == 0 ? now_ns() : 0;
-            mbar_wait(empty_s(j), sphase ^ 1);
-            const unsigned long long g0 = traced && gt == 0 ? now_ns() : 0;
-            const long long c0 = traced && gt == 0 ? clock64() : 0;
-            if (traced && gt == 0) wait_e += g0 - w0;
-            if (pushing && gt == 0) mbar_expect_tx(full_s(j), (uint32_t)((cy - 1) * my_rows * 128 * 2));   // the y-peer's block
-            uint8_t *slot = s_ring + (size_t)j * 2 * tile_bytes;
-            const int64_t kb = kb_begin + 2 * n;
-            auto chunk_at = [&](int r, int o) {     // row r of the tile, 16-byte chunk o of the slot's 256-byte row
-                return slot + (o >> 3) * tile_bytes + (r >> 3) * 1024 + (r & 7) * 128 + (((o & 7) ^ (r & 7)) << 4);
-            };
-            if (prm.debug & 1) {
-            } else if (prm.kind == 0) {
-                // One Philox call = 8 normals = one 16-byte chunk; 16 chunks per row and slot.
-                // Chunks i and i + G together while both exist (two interleaved chains), then at most one.
-                const int chunks = my_rows * 16;
-                auto put = [&](int i, const uint4 &v) { *reinterpret_cast<uint4 *>(chunk_at(place + (i >> 4), i & 15)) = v; };
-                int i = gt;
-                for (; i + kGeneratorThreads < chunks; i += 2 * kGeneratorThreads) {
-                    const int i1 = i + kGeneratorThreads;
-                    uint4 v0, v1;
-                    normal_octet2(rng, (uint32_t)(kb * 8 + (i & 15)), (uint32_t)(p0 + row0 + (i >> 4)),
-                                  (uint32_t)(kb * 8 + (i1 & 15)), (uint32_t)(p0 + row0 + (i1 >> 4)), prm.off_lo,
-                                  prm.off_hi, v0, v1);
-                    put(i, v0), put(i1, v1);
+        // One pass over the S ring; fill(slot, kb) writes this CTA's block of the slot starting at k-block kb.
+        auto for_each_slot = [&](auto &&fill) {
+            int j = 0;
+            uint32_t sphase = 0;
+            for (int n = 0; n < nslots; ++n) {
+                const unsigned long long w0 = traced && gt == 0 ? now_ns() : 0;
+                mbar_wait(empty_s(j), sphase ^ 1);
+                const unsigned long long g0 = traced && gt == 0 ? now_ns() : 0;
+                const long long c0 = traced && gt == 0 ? clock64() : 0;
+                if (traced && gt == 0) wait_e += g0 - w0;
+                if (pushing && gt == 0) mbar_expect_tx(full_s(j), (uint32_t)((cy - 1) * my_rows * 128 * 2));   // the y-peer's block
+                uint8_t *slot = s_ring + (size_t)j * 2 * tile_bytes;
+                if (!(prm.debug & 1)) fill(slot, kb_begin + 2 * n);
+                const long long c1 = traced && gt == 0 ? clock64() : 0;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
+                const long long c2 = traced && gt == 0 ? clock64() : 0;
+                if (pushing) {
+                    // all generator threads have written (and fenced) this CTA's block: push both halves to the y-peers
+                    asm volatile("bar.sync 1, %0;" ::"n"(kGeneratorThreads) : "memory");
+                    if (gt == 0) {
+                        for (uint32_t y = 0; y < (uint32_t)cy; ++y)
+                            if (y != ry)
+                                for (uint32_t h = 0; h < 2; ++h) {
+                                    const uint32_t block = smem_addr(slot) + h * tile_bytes + row0 * 128;
+                                    bulk_copy_to_peer(map_to_cta(block, group0 + y), block, my_rows * 128, map_to_cta(full_s(j), group0 + y));
+                                }
+                    }
                 }
-                if (i < chunks)
-                    put(i, normal_octet(rng, (uint32_t)(kb * 8 + (i & 15)), (uint32_t)(p0 + row0 + (i >> 4)), prm.off_lo,
-                                        prm.off_hi));
-            } else {
-                // One Philox call = 128 signs = one row of the slot.  A task expands one of its four words
-                // (32 tokens = four chunks); the four tasks of a row repeat the call in neighbouring lanes,
-                // which costs nothing in a SIMT warp and keeps 4 x rows threads busy.
+                __syncwarp();
+                const long long c3 = traced && gt == 0 ? clock64() : 0;
+                if (traced && gt == 0) ph[0] += c1 - c0, ph[1] += c2 - c1, ph[2] += c3 - c2;
+                if (traced && gt == 0) busy += now_ns() - g0;
+                if (lane == 0) mbar_arrive(full_s(j));       // pair mode, second CTA: warp 1 forwards it
+                if (traced && gt == 0) ph[3] += clock64() - c3;
+                if (++j == slots) j = 0, sphase ^= 1;
+            }
+        };
+        // row r of the tile, 16-byte chunk o of the slot's 256-byte row (K-major SW128: chunk XOR row mod 8)
+        auto chunk_at = [&](uint8_t *slot, int r, int o) {
+            return slot + (o >> 3) * tile_bytes + (r >> 3) * 1024 + (r & 7) * 128 + (((o & 7) ^ (r & 7)) << 4);
+        };
+        // Gaussian, up to four chunks per thread: a thread's chunks sit at the same (row, chunk) of every
+        // slot, and the Philox calls of the NEXT slot are made in the same straight-line block as the
+        // Box-Muller evaluations of this one -- integer multiply-xor rounds and MUFU chains interleave,
+        // where one after the other they leave the ALU and the XU pipes idle in turn.
+        auto gaussian_pipelined = [&](auto count) {
+            constexpr int kPer = decltype(count)::value;
+            const bool working = gt < active;
+            uint32_t o[kPer], p[kPer];
+            uint4 c[kPer];
+            int at[kPer];
+#pragma unroll
+            for (int q = 0; q < kPer; ++q) {
+                at[q] = min(gt + q * active, chunks - 1);        // a duplicate at the ragged end
+                o[q] = (uint32_t)(at[q] & 15), p[q] = (uint32_t)(p0 + row0 + (at[q] >> 4));
+                c[q] = rng(make_uint4((uint32_t)(kb_begin * 8) + o[q], p[q], prm.off_lo, prm.off_hi));
+            }
+            for_each_slot([&](uint8_t *slot, int64_t kb) {
+                if (!working) return;
+                uint4 v[kPer], next[kPer];
+#pragma unroll
+                for (int q = 0; q < kPer; ++q) next[q] = make_uint4((uint32_t)((kb + 2) * 8) + o[q], p[q], prm.off_lo, prm.off_hi);
+                philox_and_normals<kPer>(rng, next, c, v, prm.zero);
+#pragma unroll
+                for (int q = 0; q < kPer; ++q) {
+                    *reinterpret_cast<uint4 *>(chunk_at(slot, place + (at[q] >> 4), at[q] & 15)) = v[q];
+                    c[q] = next[q];
+                }
+            });
+        };
+        if (prm.kind == 0 && per <= 4) {
+            switch (per) {
+                case 1: gaussian_pipelined(std::integral_constant<int, 1>{}); break;
+                case 2: gaussian_pipelined(std::integral_constant<int, 2>{}); break;
+                case 3: gaussian_pipelined(std::integral_constant<int, 3>{}); break;
+                default: gaussian_pipelined(std::integral_constant<int, 4>{}); break;
+            }
+        } else if (prm.kind == 0) {
+            // more than four chunks per thread (BN rows unshared): groups of up to four interleaved chains
+            for_each_slot([&](uint8_t *slot, int64_t kb) {
+                if (gt >= active) return;
+                auto run = [&](auto count, int q0) {
+                    constexpr int kCount = decltype(count)::value;
+                    uint32_t o[kCount], p[kCount];
+                    uint4 v[kCount];
+                    int at[kCount];
+#pragma unroll
+                    for (int q = 0; q < kCount; ++q) {
+                        at[q] = min(gt + (q0 + q) * active, chunks - 1);
+                        o[q] = (uint32_t)(kb * 8 + (at[q] & 15)), p[q] = (uint32_t)(p0 + row0 + (at[q] >> 4));
+                    }
+                    normal_octets<kCount>(rng, o, p, prm.off_lo, prm.off_hi, v);
+#pragma unroll
+                    for (int q = 0; q < kCount; ++q)
+                        *reinterpret_cast<uint4 *>(chunk_at(slot, place + (at[q] >> 4), at[q] & 15)) = v[q];
+                };
+                for (int q0 = 0; q0 < per; q0 += group) {
+                    switch (min(group, per - q0)) {
+                        case 1: run(std::integral_constant<int, 1>{}, q0); break;
+                        case 2: run(std::integral_constant<int, 2>{}, q0); break;
+                        case 3: run(std::integral_constant<int, 3>{}, q0); break;
+                        default: run(std::integral_constant<int, 4>{}, q0); break;
+                    }
+                }
+            });
+        } else {
+            // One Philox call = 128 signs = one row of the slot.  A task expands one of its four words
+            // (32 tokens = four chunks); the four tasks of a row repeat the call in neighbouring lanes,
+            // which costs nothing in a SIMT warp and keeps 4 x rows threads busy.
+            for_each_slot([&](uint8_t *slot, int64_t kb) {
                 for (int task = gt; task < 4 * my_rows; task += kGeneratorThreads) {
                     const int row = task >> 2, q = task & 3;
                     const uint4 w = sign_block(rng, (uint32_t)(kb >> 1), (uint32_t)(p0 + row0 + row), prm.off_lo, prm.off_hi);
@@ -606,33 +739,11 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const uint32_t bits = word >> (c * 8);
-                        *reinterpret_cast<uint4 *>(chunk_at(place + row, q * 4 + c)) =
+                        *reinterpret_cast<uint4 *>(chunk_at(slot, place + row, q * 4 + c)) =
                             make_uint4(sign_pair(bits), sign_pair(bits >> 2), sign_pair(bits >> 4), sign_pair(bits >> 6));
                     }
                 }
-            }
-            const long long c1 = traced && gt == 0 ? clock64() : 0;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
-            const long long c2 = traced && gt == 0 ? clock64() : 0;
-            if (pushing) {
-                // all generator threads have written (and fenced) this CTA's block: push both halves to the y-peers
-                asm volatile("bar.sync 1, %0;" ::"n"(kGeneratorThreads) : "memory");
-                if (gt == 0) {
-                    for (uint32_t y = 0; y < (uint32_t)cy; ++y)
-                        if (y != ry)
-                            for (uint32_t h = 0; h < 2; ++h) {
-                                const uint32_t block = smem_addr(slot) + h * tile_bytes + row0 * 128;
-                                bulk_copy_to_peer(map_to_cta(block, y), block, my_rows * 128, map_to_cta(full_s(j), y));
-                            }
-                }
-            }
-            __syncwarp();
-            const long long c3 = traced && gt == 0 ? clock64() : 0;
-            if (traced && gt == 0) ph[0] += c1 - c0, ph[1] += c2 - c1, ph[2] += c3 - c2;
-            if (traced && gt == 0) busy += now_ns() - g0;
-            if (lane == 0) mbar_arrive(full_s(j));       // pair mode, second CTA: warp 1 forwards it
-            if (traced && gt == 0) ph[3] += clock64() - c3;
-            if (++j == slots) j = 0, sphase ^= 1;
+            });
         }
         if (traced && gt == 0) prm.trace[8] = wait_e, prm.trace[9] = now_ns(), prm.trace[10] = busy;
         if (traced && gt == 0)
@@ -642,35 +753,43 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     // All warps: a warp reads the TMEM lanes of its quadrant (warp % 4); the warps of a
     // quadrant share its (feature block, 16-column) units.  For a fixed sketch row the 32 lanes
     // hold 32 consecutive features: every store instruction writes one 128-byte line.
+    mbar_wait(accum_full, 0);
+    if (traced && warp == 4 && lane == 0) prm.trace[4] = now_ns();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int quarter = warp & 3;                       // TMEM lanes [32q, 32q + 32)
+    const int units_per_block = bn / 16;
+    auto load_unit = [&](int m, int c, uint32_t (&v)[16]) {      // 16 sketch rows of this lane's feature (asynchronous)
+        tmem_load16(tmem_base + ((uint32_t)(quarter * 32) << 16) + m * kMaxRows + c * 16, v);
+    };
+    auto store_unit = [&](float *out, int m, int c, const uint32_t (&v)[16], float scale) {
+        const int d = d0 + m * 128 + quarter * 32 + lane;
+        if (d < prm.features) {
+            float *dst = out + (int64_t)(p0 + c * 16) * prm.features + d;
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+                if (p0 + c * 16 + q < prm.rows) dst[(int64_t)q * prm.features] = iters ? __uint_as_float(v[q]) * scale : 0.0f;
+        }
+    };
     {
-        mbar_wait(accum_full, 0);
-        if (traced && warp == 4 && lane == 0) prm.trace[4] = now_ns();
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int quarter = warp & 3;                       // TMEM lanes [32q, 32q + 32)
+        // split_k == 1: the result; else this split's partial, added up by reduce_splits_kernel
         float *out = prm.out + (prm.split_k > 1 ? (int64_t)blockIdx.z * prm.rows * prm.features : 0);
         const float scale = prm.split_k > 1 ? 1.0f : prm.scale;
-        const int units_per_block = bn / 16;
-        for (int t = warp >> 2; t < nblocks * units_per_block; t += kThreads / 128) {
-            const int m = t / units_per_block, c = (t % units_per_block) * 16;
-            const int d = d0 + m * 128 + quarter * 32 + lane;
-            uint32_t v[16];
-            tmem_load16(tmem_base + ((uint32_t)(quarter * 32) << 16) + m * kMaxRows + c, v);
-            if (iters == 0) {
-#pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = 0;
-            }
-            if (d < prm.features) {
-                float *dst = out + (int64_t)(p0 + c) * prm.features + d;
-#pragma unroll
-                for (int q = 0; q < 16; ++q)
-                    if (p0 + c + q < prm.rows) dst[(int64_t)q * prm.features] = __uint_as_float(v[q]) * scale;
-            }
+        // two units in flight per warp: the second TMEM read overlaps the first unit's stores
+        const int total = nblocks * units_per_block, step = kThreads / 128;
+        for (int t = warp >> 2; t < total; t += 2 * step) {
+            uint32_t v[16], w[16] = {};
+            const bool two = t + step < total;
+            load_unit(t / units_per_block, t % units_per_block, v);
+            if (two) load_unit((t + step) / units_per_block, (t + step) % units_per_block, w);
+            tmem_load_wait(v, w);
+            store_unit(out, t / units_per_block, t % units_per_block, v, scale);
+            if (two) store_unit(out, (t + step) / units_per_block, (t + step) % units_per_block, w, scale);
         }
     }
     if (traced && warp == 4 && lane == 0) prm.trace[5] = now_ns();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (kPair || cy > 1) cluster_sync();      // nobody leaves while peers may still signal it
+    if (clustered) cluster_sync();            // nobody leaves while peers may still signal it
     if (warp == 1) {
         if constexpr (kPair)
             asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -681,13 +800,21 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     }
 }
 
-__global__ void reduce_splits_kernel(const float *partials, float *out, int64_t count, int splits,
-                                     float scale) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        float acc = 0.0f;
-        for (int s = 0; s < splits; ++s) acc += partials[(int64_t)s * count + i];
-        out[i] = acc * scale;
+// out = scale * sum of the split-K partials (fixed order: deterministic).  kVec = 4 when the buffers allow float4.
+template <int kVec>
+__global__ void reduce_splits_kernel(const float *partials, float *out, int64_t count, int splits, float scale) {
+    using Vec = typename std::conditional<kVec == 4, float4, float>::type;
+    const int64_t n = count / kVec;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        Vec acc = reinterpret_cast<const Vec *>(partials)[i];
+        for (int s = 1; s < splits; ++s) {
+            const Vec v = __ldcs(reinterpret_cast<const Vec *>(partials + (int64_t)s * count) + i);
+            if constexpr (kVec == 4) acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+            else acc += v;
+        }
+        if constexpr (kVec == 4) acc.x *= scale, acc.y *= scale, acc.z *= scale, acc.w *= scale;
+        else acc *= scale;
+        reinterpret_cast<Vec *>(out)[i] = acc;
     }
 }
 
@@ -743,7 +870,7 @@ struct Plan {
     int bn, split_k, cy;
     bool pair;
     int kblocks_per_split;       // even: an S slot spans two 64-token stages
-    int x_units, s_slots, s_tile_bytes, smem_bytes;
+    int s_slots, s_tile_bytes, smem_bytes;
 };
 
 static int env_int(const char *name, int fallback) {
@@ -763,8 +890,7 @@ static Plan plan(int rows, int features, int64_t tokens, int kind, int sms) {
     // Measured (profiles/r01_sketch_kernel.md): with Gaussian entries the kernel is bound by generating
     // S and the pair halves that work (D = 3072: 493 -> 406 us); with Rademacher entries it is bound by
     // the MMA pipeline, and the extra hop of the peer's "S ready" signal costs more than it saves.
-    pl.pair = features % (2 * kFeaturesPerCta) == 0 && kind == 0;
-    pl.pair = pl.pair && env_int("FEWBIT_B200_SKETCH_PAIR", 1) != 0;
+    pl.pair = features % (2 * kFeaturesPerCta) == 0 && env_int("FEWBIT_B200_SKETCH_PAIR", 1) != 0;   // 0: A/B runs
     if (pl.pair) pl.cy = 2;
     if (const int v = env_int("FEWBIT_B200_SKETCH_CLUSTER", 0)) {   // A/B runs: Cy without cta_group::2
         if (v >= 1 && v <= 2) pl.cy = std::min(pl.cy, v);
@@ -796,15 +922,14 @@ static Plan plan(int rows, int features, int64_t tokens, int kind, int sms) {
     }
     int per = (int)((kblocks + pl.split_k - 1) / pl.split_k);
     pl.kblocks_per_split = per + (per & 1);
-    // Shared memory: the S ring first (each CTA stores only the rows it generates in pair mode, the
-    // whole BN-row slot otherwise), the X ring gets what is left.
+    // Shared memory: three X stages, the rest holds S slots (each CTA stores only the rows it generates
+    // in pair mode, the whole BN-row slot otherwise).
     const int tile_rows = ((pl.pair ? pl.bn / 2 : pl.bn) + 7) / 8 * 8;
     pl.s_tile_bytes = tile_rows * 128;
-    pl.s_slots = std::min(kMaxSlots, std::max(1, env_int("FEWBIT_B200_SKETCH_SLOTS", pl.pair ? 3 : 2)));
-    const int room = kSmemLimit - 1024 /* alignment */ - kBarrierBytes - pl.s_slots * 2 * pl.s_tile_bytes;
-    pl.x_units = std::min(kMaxUnits, room / kUnitBytes);
-    if (const int v = env_int("FEWBIT_B200_SKETCH_UNITS", 0)) pl.x_units = std::min(pl.x_units, std::max(v, 1));
-    pl.smem_bytes = pl.x_units * kUnitBytes + pl.s_slots * 2 * pl.s_tile_bytes + kBarrierBytes + 1024;
+    const int room = kSmemLimit - 1024 /* alignment */ - kBarrierBytes - kStages * kXStageBytes;
+    pl.s_slots = std::min(kMaxSlots, room / (2 * pl.s_tile_bytes));
+    if (const int v = env_int("FEWBIT_B200_SKETCH_SLOTS", 0)) pl.s_slots = std::min(pl.s_slots, std::max(v, 1));
+    pl.smem_bytes = kStages * kXStageBytes + pl.s_slots * 2 * pl.s_tile_bytes + kBarrierBytes + 1024;
     return pl;
 }
 
@@ -836,8 +961,7 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
     const Plan pl = plan(rows, features, tokens, kind, sm_count());
     const int bn = pl.bn, split_k = pl.split_k, cy = pl.cy;
     const bool pair = pl.pair;
-    if (split_k > 1 && !workspace) return FEWBIT_EINVAL;
-    if (pl.x_units < 3) return (int)cudaErrorInvalidConfiguration;
+    if (pl.s_slots < 1) return (int)cudaErrorInvalidConfiguration;
 
     CUtensorMap map;
     const cuuint64_t dims[2] = {(cuuint64_t)features, (cuuint64_t)std::max<int64_t>(tokens, 1)};
@@ -853,8 +977,7 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
     prm.tokens = tokens, prm.features = features, prm.rows = rows, prm.block_rows = bn;
     prm.kblocks_per_split = pl.kblocks_per_split;
     prm.split_k = split_k, prm.scale = scale, prm.kind = kind, prm.cluster_y = cy;
-    prm.x_units = pl.x_units, prm.s_slots = pl.s_slots, prm.s_tile_bytes = pl.s_tile_bytes;
-    prm.prefetch = env_int("FEWBIT_B200_SKETCH_PREFETCH", 0);
+    prm.s_slots = pl.s_slots, prm.s_tile_bytes = pl.s_tile_bytes, prm.zero = 0;
     prm.debug = env_int("FEWBIT_B200_SKETCH_DEBUG", 0);
     prm.trace = nullptr;
     static unsigned long long *trace_buffer = nullptr;
@@ -888,6 +1011,7 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = pair ? 2 : 1, attr[0].val.clusterDim.y = pair ? 1 : cy, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
+    if (split_k > 1 && !workspace) return FEWBIT_EINVAL;
     cudaError_t launched = pair ? cudaLaunchKernelEx(&cfg, sketch_kernel<true>, map, prm)
                                 : cudaLaunchKernelEx(&cfg, sketch_kernel<false>, map, prm);
     if (launched != cudaSuccess) return (int)launched;
@@ -897,18 +1021,20 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
         cudaStreamSynchronize(s);
         cudaMemcpy(t, trace_buffer, sizeof(t), cudaMemcpyDeviceToHost);
         std::fprintf(stderr,
-                     "[sketch trace] D=%d bn=%d split_k=%d pair=%d units=%d slots=%d grid=%ux%ux%u | setup %.1f us, first MMA +%.1f, "
+                     "[sketch trace] D=%d bn=%d split_k=%d pair=%d slots=%d grid=%ux%ux%u | setup %.1f us, first MMA +%.1f, "
                      "MMA loop %.1f (waited X %.1f, S %.1f), generators done +%.1f (waited empty %.1f, generating %.1f), "
                      "accumulators seen +%.1f, epilogue %.1f | generator thread 0, cycles per 128-token slot: generate %llu, proxy fence %llu, "
                      "sync+push %llu, arrive %llu\n",
-                     features, bn, split_k, (int)pair, pl.x_units, pl.s_slots, cfg.gridDim.x, cfg.gridDim.y, cfg.gridDim.z,
+                     features, bn, split_k, (int)pair, pl.s_slots, cfg.gridDim.x, cfg.gridDim.y, cfg.gridDim.z,
                      (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3, t[6] * 1e-3, t[7] * 1e-3,
                      (t[9] - t[1]) * 1e-3, t[8] * 1e-3, t[10] * 1e-3, (t[4] - t[1]) * 1e-3, (t[5] - t[4]) * 1e-3, t[11], t[12], t[13], t[14]);
     }
     if (split_k > 1) {
         const int64_t count = (int64_t)rows * features;
-        reduce_splits_kernel<<<(unsigned)std::min<int64_t>((count + 255) / 256, sm_count() * 8), 256, 0, s>>>(
-            static_cast<const float *>(workspace), out, count, split_k, scale);
+        const bool wide = count % 4 == 0 && ((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+        const unsigned blocks = (unsigned)std::min<int64_t>((count / (wide ? 4 : 1) + 255) / 256, sm_count() * 8);
+        if (wide) reduce_splits_kernel<4><<<blocks, 256, 0, s>>>(static_cast<const float *>(workspace), out, count, split_k, scale);
+        else reduce_splits_kernel<1><<<blocks, 256, 0, s>>>(static_cast<const float *>(workspace), out, count, split_k, scale);
         note_launch();
     }
     return (int)cudaGetLastError();
