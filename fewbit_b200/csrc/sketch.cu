@@ -212,6 +212,20 @@ __device__ __forceinline__ uint32_t cluster_cta_rank() {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
+__device__ __forceinline__ void cluster_arrive() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Programmatic dependent launch: let the next kernel of the stream (the split-K reduction) be
+// scheduled while this grid drains / wait until the previous grid has completed and flushed.
+__device__ __forceinline__ void launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void wait_for_primary() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -487,8 +501,14 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    // Peers' barriers must exist before anyone signals them.  Generator warps that only touch their own
+    // CTA (every mode but `pushing`) start at once and complete this cluster barrier after their loop.
     const bool clustered = kPair || cy > 1;
-    if (clustered) cluster_sync();            // peers' barriers exist before anyone signals them
+    const bool late_wait = clustered && !pushing && warp >= 2;
+    if (clustered) {
+        cluster_arrive();
+        if (!late_wait) cluster_wait();
+    }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     if (traced && threadIdx.x == 0) prm.trace[1] = now_ns();
@@ -745,6 +765,7 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
                 }
             });
         }
+        if (late_wait) cluster_wait();
         if (traced && gt == 0) prm.trace[8] = wait_e, prm.trace[9] = now_ns(), prm.trace[10] = busy;
         if (traced && gt == 0)
             for (int q = 0; q < 4; ++q) prm.trace[11 + q] = (unsigned long long)(ph[q] / max(nslots, 1));
@@ -754,6 +775,7 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     // quadrant share its (feature block, 16-column) units.  For a fixed sketch row the 32 lanes
     // hold 32 consecutive features: every store instruction writes one 128-byte line.
     mbar_wait(accum_full, 0);
+    if (prm.split_k > 1) launch_dependents();
     if (traced && warp == 4 && lane == 0) prm.trace[4] = now_ns();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int quarter = warp & 3;                       // TMEM lanes [32q, 32q + 32)
@@ -805,6 +827,7 @@ template <int kVec>
 __global__ void reduce_splits_kernel(const float *partials, float *out, int64_t count, int splits, float scale) {
     using Vec = typename std::conditional<kVec == 4, float4, float>::type;
     const int64_t n = count / kVec;
+    wait_for_primary();              // launched early (programmatic stream serialisation): the partials are complete from here
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         Vec acc = reinterpret_cast<const Vec *>(partials)[i];
         for (int s = 1; s < splits; ++s) {
@@ -1033,8 +1056,16 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
         const int64_t count = (int64_t)rows * features;
         const bool wide = count % 4 == 0 && ((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
         const unsigned blocks = (unsigned)std::min<int64_t>((count / (wide ? 4 : 1) + 255) / 256, sm_count() * 8);
-        if (wide) reduce_splits_kernel<4><<<blocks, 256, 0, s>>>(static_cast<const float *>(workspace), out, count, split_k, scale);
-        else reduce_splits_kernel<1><<<blocks, 256, 0, s>>>(static_cast<const float *>(workspace), out, count, split_k, scale);
+        cudaLaunchConfig_t rcfg{};
+        rcfg.gridDim = dim3(blocks), rcfg.blockDim = dim3(256), rcfg.stream = s;
+        cudaLaunchAttribute early[1];
+        early[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        early[0].val.programmaticStreamSerializationAllowed = 1;
+        rcfg.attrs = early, rcfg.numAttrs = 1;
+        const float *partials = static_cast<const float *>(workspace);
+        const cudaError_t reduced = wide ? cudaLaunchKernelEx(&rcfg, reduce_splits_kernel<4>, partials, out, count, split_k, scale)
+                                         : cudaLaunchKernelEx(&rcfg, reduce_splits_kernel<1>, partials, out, count, split_k, scale);
+        if (reduced != cudaSuccess) return (int)reduced;
         note_launch();
     }
     return (int)cudaGetLastError();
