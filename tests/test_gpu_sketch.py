@@ -44,7 +44,9 @@ def test_sketch_matrix_statistics(kind):
 SHAPES = [(64, 8, 16), (1000, 72, 50), (4096, 384, 160), (4100, 392, 161), (2048, 768, 333),
           (16384, 768, 3276), (3000, 3072, 600), (777, 1024, 1),
           # feature counts that are multiples of 768 run on CTA pairs (Gaussian): edge shapes of that mode
-          (100, 768, 1), (64, 1536, 17), (130, 2304, 161), (8200, 768, 145)]
+          (100, 768, 1), (64, 1536, 17), (130, 2304, 161), (8200, 768, 145),
+          # S slots span two 64-token stages: odd stage counts, a single token, the two-tile push mode over many slots
+          (192, 768, 20), (1, 768, 3), (5000, 512, 300), (8000, 3072, 64)]
 
 
 @pytest.mark.parametrize('rows,cols,seed,offset', [(5, 300, 42, 4), (161, 4100, 2 ** 40 + 3, 2 ** 33 + 9),
