@@ -4,7 +4,9 @@ Every element is independent, and the packed stream of a concatenation is the co
 of the packed streams whenever each shard holds a multiple of 8 elements (8 elements <-> `bits`
 whole bytes).  So N GPUs process N contiguous shards with no collective on the data path; the
 packed state is consumed by the backward pass on the GPU that produced it.  ``shard_bounds``
-is the partition rule used by bench.py and the multi-process tests.
+is the partition rule for a caller that splits ONE tensor over ranks (tests/test_distributed.py,
+tests/test_properties.py); bench.py scales weakly -- every rank owns a whole 1 GiB tensor -- and
+needs no partition.
 """
 from __future__ import annotations
 
