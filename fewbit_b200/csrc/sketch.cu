@@ -99,6 +99,7 @@ constexpr int kSmemLimit = 232448;                            // 227 KB per CTA
 constexpr int kGeneratorWarps = kThreads / 32 - 2;
 constexpr int kGeneratorThreads = kGeneratorWarps * 32;
 constexpr int kTmemColumns = 512;
+constexpr uint32_t kOnes = 0x3f803f80u;                       // two bf16 ones
 
 // ---------------------------------------------------------------------------- PTX ----
 
@@ -409,7 +410,9 @@ __device__ __forceinline__ unsigned long long now_ns() {
 }
 
 struct Params {
-    float *out;          // [P, D] (split_k == 1) or partials [split_k, P, D]
+    float *out;          // [P, D] (split_k == 1; bf16 if out_bf16) or fp32 partials [split_k, P, D]
+    int out_bf16;        // the result is written as bf16
+    int ones_row;        // this row of S is all ones (its output row = column sums of X), -1: none
     int64_t tokens;      // N
     int features;        // D
     int rows;            // P
@@ -707,6 +710,7 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
                 philox_and_normals<kPer>(rng, next, c, v, prm.zero);
 #pragma unroll
                 for (int q = 0; q < kPer; ++q) {
+                    if ((int)p[q] == prm.ones_row) v[q] = make_uint4(kOnes, kOnes, kOnes, kOnes);
                     *reinterpret_cast<uint4 *>(chunk_at(slot, place + (at[q] >> 4), at[q] & 15)) = v[q];
                     c[q] = next[q];
                 }
@@ -735,8 +739,10 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
                     }
                     normal_octets<kCount>(rng, o, p, prm.off_lo, prm.off_hi, v);
 #pragma unroll
-                    for (int q = 0; q < kCount; ++q)
+                    for (int q = 0; q < kCount; ++q) {
+                        if ((int)p[q] == prm.ones_row) v[q] = make_uint4(kOnes, kOnes, kOnes, kOnes);
                         *reinterpret_cast<uint4 *>(chunk_at(slot, place + (at[q] >> 4), at[q] & 15)) = v[q];
+                    }
                 };
                 for (int q0 = 0; q0 < per; q0 += group) {
                     switch (min(group, per - q0)) {
@@ -756,11 +762,13 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
                     const int row = task >> 2, q = task & 3;
                     const uint4 w = sign_block(rng, (uint32_t)(kb >> 1), (uint32_t)(p0 + row0 + row), prm.off_lo, prm.off_hi);
                     const uint32_t word = q == 0 ? w.x : q == 1 ? w.y : q == 2 ? w.z : w.w;
+                    const bool ones = p0 + row0 + row == prm.ones_row;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const uint32_t bits = word >> (c * 8);
                         *reinterpret_cast<uint4 *>(chunk_at(slot, place + row, q * 4 + c)) =
-                            make_uint4(sign_pair(bits), sign_pair(bits >> 2), sign_pair(bits >> 4), sign_pair(bits >> 6));
+                            ones ? make_uint4(kOnes, kOnes, kOnes, kOnes)
+                                 : make_uint4(sign_pair(bits), sign_pair(bits >> 2), sign_pair(bits >> 4), sign_pair(bits >> 6));
                     }
                 }
             });
@@ -783,13 +791,18 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     auto load_unit = [&](int m, int c, uint32_t (&v)[16]) {      // 16 sketch rows of this lane's feature (asynchronous)
         tmem_load16(tmem_base + ((uint32_t)(quarter * 32) << 16) + m * kMaxRows + c * 16, v);
     };
+    const bool narrow = prm.out_bf16 && prm.split_k == 1;        // partials are always fp32
     auto store_unit = [&](float *out, int m, int c, const uint32_t (&v)[16], float scale) {
         const int d = d0 + m * 128 + quarter * 32 + lane;
         if (d < prm.features) {
-            float *dst = out + (int64_t)(p0 + c * 16) * prm.features + d;
+            const int64_t at = (int64_t)(p0 + c * 16) * prm.features + d;
 #pragma unroll
-            for (int q = 0; q < 16; ++q)
-                if (p0 + c * 16 + q < prm.rows) dst[(int64_t)q * prm.features] = iters ? __uint_as_float(v[q]) * scale : 0.0f;
+            for (int q = 0; q < 16; ++q) {
+                if (p0 + c * 16 + q >= prm.rows) continue;
+                const float value = iters ? __uint_as_float(v[q]) * scale : 0.0f;
+                if (narrow) reinterpret_cast<__nv_bfloat16 *>(out)[at + (int64_t)q * prm.features] = __float2bfloat16_rn(value);
+                else out[at + (int64_t)q * prm.features] = value;
+            }
         }
     };
     {
@@ -822,9 +835,10 @@ sketch_kernel(const __grid_constant__ CUtensorMap x_map, const Params prm) {
     }
 }
 
-// out = scale * sum of the split-K partials (fixed order: deterministic).  kVec = 4 when the buffers allow float4.
-template <int kVec>
-__global__ void reduce_splits_kernel(const float *partials, float *out, int64_t count, int splits, float scale) {
+// out = scale * sum of the split-K partials (fixed order: deterministic), fp32 or bf16.  kVec = 4 when the
+// buffers allow 16-byte loads.
+template <int kVec, typename Out>
+__global__ void reduce_splits_kernel(const float *partials, Out *out, int64_t count, int splits, float scale) {
     using Vec = typename std::conditional<kVec == 4, float4, float>::type;
     const int64_t n = count / kVec;
     wait_for_primary();              // launched early (programmatic stream serialisation): the partials are complete from here
@@ -835,9 +849,17 @@ __global__ void reduce_splits_kernel(const float *partials, float *out, int64_t 
             if constexpr (kVec == 4) acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
             else acc += v;
         }
-        if constexpr (kVec == 4) acc.x *= scale, acc.y *= scale, acc.z *= scale, acc.w *= scale;
-        else acc *= scale;
-        reinterpret_cast<Vec *>(out)[i] = acc;
+        if constexpr (kVec == 4) {
+            acc.x *= scale, acc.y *= scale, acc.z *= scale, acc.w *= scale;
+            if constexpr (std::is_same<Out, float>::value) {
+                reinterpret_cast<float4 *>(out)[i] = acc;
+            } else {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
+                reinterpret_cast<uint2 *>(out)[i] = make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi));
+            }
+        } else {
+            out[i] = static_cast<Out>(acc * scale);
+        }
     }
 }
 
@@ -975,7 +997,16 @@ size_t fewbit_sketch_workspace_bytes(int64_t tokens, int features, int rows) {
 
 int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t tokens, int features,
                           int rows, int kind, float scale, uint64_t seed, uint64_t offset, void *stream) {
-    if (tokens < 0 || features <= 0 || rows <= 0 || (kind != 0 && kind != 1)) return FEWBIT_EINVAL;
+    return fewbit_sketch_project(x, out, FEWBIT_F32, workspace, tokens, features, rows, 0, kind, scale, seed, offset, stream);
+}
+
+int fewbit_sketch_project(const void *x, void *out_any, int out_dtype, void *workspace, int64_t tokens, int features,
+                          int sketch_rows, int column_sums, int kind, float scale, uint64_t seed, uint64_t offset,
+                          void *stream) {
+    if (tokens < 0 || features <= 0 || sketch_rows <= 0 || (kind != 0 && kind != 1)) return FEWBIT_EINVAL;
+    if (out_dtype != FEWBIT_F32 && out_dtype != FEWBIT_BF16) return FEWBIT_EDTYPE;
+    float *out = static_cast<float *>(out_any);
+    const int rows = sketch_rows + (column_sums ? 1 : 0);      // the extra row of S is all ones
     if (!x || !out) return FEWBIT_EINVAL;
     if (features % 8 != 0 || (reinterpret_cast<uintptr_t>(x) & 15)) return FEWBIT_EALIGN;  // TMA strides
     EncodeTiled encode = encode_tiled();
@@ -1001,6 +1032,7 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
     prm.kblocks_per_split = pl.kblocks_per_split;
     prm.split_k = split_k, prm.scale = scale, prm.kind = kind, prm.cluster_y = cy;
     prm.s_slots = pl.s_slots, prm.s_tile_bytes = pl.s_tile_bytes, prm.zero = 0;
+    prm.out_bf16 = out_dtype == FEWBIT_BF16, prm.ones_row = column_sums ? sketch_rows : -1;
     prm.debug = env_int("FEWBIT_B200_SKETCH_DEBUG", 0);
     prm.trace = nullptr;
     static unsigned long long *trace_buffer = nullptr;
@@ -1063,8 +1095,12 @@ int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t to
         early[0].val.programmaticStreamSerializationAllowed = 1;
         rcfg.attrs = early, rcfg.numAttrs = 1;
         const float *partials = static_cast<const float *>(workspace);
-        const cudaError_t reduced = wide ? cudaLaunchKernelEx(&rcfg, reduce_splits_kernel<4>, partials, out, count, split_k, scale)
-                                         : cudaLaunchKernelEx(&rcfg, reduce_splits_kernel<1>, partials, out, count, split_k, scale);
+        __nv_bfloat16 *narrow = static_cast<__nv_bfloat16 *>(out_any);
+        const cudaError_t reduced =
+            prm.out_bf16 ? (wide ? cudaLaunchKernelEx(&rcfg, reduce_splits_kernel<4, __nv_bfloat16>, partials, narrow, count, split_k, scale)
+                                 : cudaLaunchKernelEx(&rcfg, reduce_splits_kernel<1, __nv_bfloat16>, partials, narrow, count, split_k, scale))
+                         : (wide ? cudaLaunchKernelEx(&rcfg, reduce_splits_kernel<4, float>, partials, out, count, split_k, scale)
+                                 : cudaLaunchKernelEx(&rcfg, reduce_splits_kernel<1, float>, partials, out, count, split_k, scale));
         if (reduced != cudaSuccess) return (int)reduced;
         note_launch();
     }

@@ -301,7 +301,10 @@ Tensor quantize_backward(const Tensor &grads, const Tensor &buffer, const Tensor
 // out[rows, D] = scale * S[rows, N] x[N, D], S generated inside the tcgen05 kernel from
 // (seed, offset); replaces randn + matmul of LinearGRPFunc (fewbit/functional/linear.py:133-137).
 
-Tensor sketch(const Tensor &x, int64_t rows, int64_t seed, int64_t offset, int64_t kind, double scale) {
+// sketch_to: the result in fp32 or bf16 (rounded once, in the kernel), and with `column_sums` one more
+// row = scale * x.sum(0), the bias gradient of LinearGRPFunc.backward (fewbit/functional/linear.py:217).
+Tensor sketch_to(const Tensor &x, int64_t rows, int64_t seed, int64_t offset, int64_t kind, double scale,
+                 bool bf16_out, bool column_sums) {
     TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.is_contiguous(),
                 "fewbit::sketch: expected a contiguous 2-D CUDA tensor [tokens, features]");
     TORCH_CHECK(x.scalar_type() == torch::kBFloat16, "fewbit::sketch: x must be bfloat16, got ", x.scalar_type());
@@ -309,14 +312,19 @@ Tensor sketch(const Tensor &x, int64_t rows, int64_t seed, int64_t offset, int64
     TORCH_CHECK(rows > 0, "fewbit::sketch: rows must be positive");
     c10::cuda::CUDAGuard guard(x.device());
     auto stream = at::cuda::getCurrentCUDAStream();
-    Tensor out = torch::empty({rows, x.size(1)}, x.options().dtype(torch::kFloat32));
-    const size_t nbytes = fewbit_sketch_workspace_bytes(x.size(0), (int)x.size(1), (int)rows);
+    const int64_t out_rows = rows + (column_sums ? 1 : 0);
+    Tensor out = torch::empty({out_rows, x.size(1)}, x.options().dtype(bf16_out ? torch::kBFloat16 : torch::kFloat32));
+    const size_t nbytes = fewbit_sketch_workspace_bytes(x.size(0), (int)x.size(1), (int)out_rows);
     Tensor workspace = torch::empty({(int64_t)std::max<size_t>(nbytes, 16)}, x.options().dtype(torch::kUInt8));
-    check_status(fewbit_sketch_forward(x.data_ptr(), out.data_ptr<float>(), workspace.data_ptr(), x.size(0),
-                                       (int)x.size(1), (int)rows, (int)kind, (float)scale, (uint64_t)seed,
-                                       (uint64_t)offset, stream.stream()),
+    check_status(fewbit_sketch_project(x.data_ptr(), out.data_ptr(), bf16_out ? FEWBIT_BF16 : FEWBIT_F32,
+                                       workspace.data_ptr(), x.size(0), (int)x.size(1), (int)rows, column_sums ? 1 : 0,
+                                       (int)kind, (float)scale, (uint64_t)seed, (uint64_t)offset, stream.stream()),
                  "sketch");
     return out;
+}
+
+Tensor sketch(const Tensor &x, int64_t rows, int64_t seed, int64_t offset, int64_t kind, double scale) {
+    return sketch_to(x, rows, seed, offset, kind, scale, false, false);
 }
 
 Tensor sketch_matrix(const Tensor &like, int64_t rows, int64_t cols, int64_t seed, int64_t offset, int64_t kind) {
@@ -441,6 +449,7 @@ TORCH_LIBRARY(fewbit, m) {
 
     // Not in the reference: the projection of RandomizedLinear as one operator.
     m.def("sketch(Tensor x, int rows, int seed, int offset, int kind, float scale) -> Tensor");
+    m.def("sketch_to(Tensor x, int rows, int seed, int offset, int kind, float scale, bool bf16_out, bool column_sums) -> Tensor");
     m.def("sketch_matrix(Tensor like, int rows, int cols, int seed, int offset, int kind) -> Tensor");
     m.def("stepwise_anchored(Tensor(a!) self, Tensor bounds, Tensor levels, float anchor = 0.0) -> Tensor(a!)");
 
@@ -488,5 +497,6 @@ TORCH_LIBRARY_IMPL(fewbit, CUDA, m) {
     m.impl("quantize", quantize);
     m.impl("quantize_backward", quantize_backward);
     m.impl("sketch", sketch);
+    m.impl("sketch_to", sketch_to);
     m.impl("sketch_matrix", sketch_matrix);
 }

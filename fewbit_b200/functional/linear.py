@@ -136,12 +136,16 @@ def _native_sketch_available(tensor: T.Tensor, kind: str) -> bool:
     return tensor.shape[-1] % 8 == 0 and tensor.dtype in (T.float32, T.bfloat16)
 
 
-def _native_sketch(view: T.Tensor, rows: int, seed: int, offset: int, kind: str, scale: float) -> T.Tensor:
-    """scale * S @ view  with S generated inside the kernel (fp32 result, [rows, features]).
-    Operands enter the tensor cores as bf16 (fp32 accumulation); the rounding is unbiased and
-    three orders of magnitude below the sketch's own O(1/sqrt(P)) noise."""
-    return T.ops.fewbit.sketch(view.to(T.bfloat16).contiguous(), rows, seed, offset,
-                               SKETCH_KINDS[kind], scale)
+def _native_sketch(view: T.Tensor, rows: int, seed: int, offset: int, kind: str, scale: float,
+                   dtype: T.dtype = T.float32, column_sums: bool = False) -> T.Tensor:
+    """scale * S @ view  with S generated inside the kernel, [rows, features] in `dtype` (fp32
+    accumulation, rounded once in the kernel: no separate `.to(dtype)` pass).  Operands enter the
+    tensor cores as bf16; the rounding is unbiased and three orders of magnitude below the
+    sketch's own O(1/sqrt(P)) noise.  `column_sums` appends the row scale * view.sum(0)."""
+    narrow = dtype == T.bfloat16
+    out = T.ops.fewbit.sketch_to(view.to(T.bfloat16).contiguous(), rows, seed, offset, SKETCH_KINDS[kind],
+                                 scale, narrow, column_sums)
+    return out if narrow or dtype == T.float32 else out.to(dtype)
 
 
 def _draw_stream(generator: T.Generator):
@@ -233,7 +237,7 @@ class LinearGRPFunc(T.autograd.Function):
             else:
                 seed, offset = _draw_stream(generator)
                 scale = 1.0 / proj_features if matmul == 'gaussian' else 4.0 / proj_features
-                input_proj = _native_sketch(input_view, proj_features, seed, offset, matmul, scale).to(input.dtype)
+                input_proj = _native_sketch(input_view, proj_features, seed, offset, matmul, scale, input.dtype)
                 if share_sketch:
                     shared = _SharedSketch()
                     shared.version, shared.rows, shared.kind = input._version, proj_features, matmul
@@ -265,13 +269,22 @@ class LinearGRPFunc(T.autograd.Function):
                     _SharedSketch.drop(ctx.shared_input)
                 grad_view = grad_output.reshape(-1, grad_output.shape[-1])
                 if _native_sketch_available(grad_view, ctx.matmul):
-                    grad_proj = _native_sketch(grad_view, ctx.proj_features, *ctx.stream, ctx.matmul, 1.0)
+                    # One kernel: S G rounded to the layer's precision, and -- when G is bf16 already, so
+                    # that nothing is rounded that torch's own sum would not round -- G.sum(0) as the
+                    # product of one more sketch row of ones (the bias gradient).
+                    with_bias = (bias is not None and ctx.needs_input_grad[2]
+                                 and grad_view.dtype == T.bfloat16 and input_proj.dtype == T.bfloat16)
+                    grad_proj = _native_sketch(grad_view, ctx.proj_features, *ctx.stream, ctx.matmul, 1.0,
+                                               input_proj.dtype, with_bias)
+                    if with_bias:
+                        grad_bias = grad_proj[ctx.proj_features]
+                        grad_proj = grad_proj[:ctx.proj_features]
                 else:  # feature count the TMA cannot address: same S, materialised
                     proj = T.ops.fewbit.sketch_matrix(grad_view, ctx.proj_features, grad_view.shape[0],
                                                       *ctx.stream, SKETCH_KINDS[ctx.matmul])
-                    grad_proj = proj.float() @ grad_view.float()
+                    grad_proj = (proj.float() @ grad_view.float()).to(input_proj.dtype)
                 # (S G)^T (S X): a small [out, P] x [P, in] product in the layer's own precision
-                grad_weight = grad_proj.to(input_proj.dtype).T @ input_proj
+                grad_weight = grad_proj.T @ input_proj
             elif ctx.needs_input_grad[1]:
                 generator = T.Generator(ctx.generator_device)
                 generator.set_state(ctx.generator_state)
@@ -284,7 +297,7 @@ class LinearGRPFunc(T.autograd.Function):
                     grad_weight = (grad_proj.T @ input_proj).real.to(weight.dtype)
                 else:
                     grad_weight = grad_proj.T @ input_proj
-            if bias is not None and ctx.needs_input_grad[2]:
+            if bias is not None and ctx.needs_input_grad[2] and grad_bias is None:
                 grad_bias = grad_output.reshape(-1, grad_output.shape[-1]).sum(dim=0)
         if grad_weight is not None and grad_weight.dtype != weight.dtype:
             grad_weight = grad_weight.to(weight.dtype)

@@ -42,6 +42,7 @@ PROTOTYPES = {
     'fewbit_piecewise_backward_host': (_i, [_i, _i, _vp, _vp, _vp, _i64, _d, _i64]),
     'fewbit_sketch_workspace_bytes': (C.c_size_t, [_i64, _i, _i]),
     'fewbit_sketch_forward': (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, C.c_float, C.c_uint64, C.c_uint64, _vp]),
+    'fewbit_sketch_project': (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _i, _i, C.c_float, C.c_uint64, C.c_uint64, _vp]),
     'fewbit_sketch_matrix': (_i, [_vp, _i, _i64, _i, C.c_uint64, C.c_uint64, _vp]),
     'fewbit_launch_count': (_i64, []),
 }
@@ -206,6 +207,22 @@ def sketch_forward(x, rows, seed, offset, kind='gaussian', scale=1.0, stream=Non
     check(lib().fewbit_sketch_forward(x.data_ptr(), out.data_ptr(), ws.data_ptr(), tokens, features, rows,
                                       SKETCH_KINDS.index(kind), scale, seed, offset, _stream(stream)),
           'fewbit_sketch_forward')
+    return out
+
+
+def sketch_project(x, rows, seed, offset, kind='gaussian', scale=1.0, out_dtype=torch.float32, column_sums=False,
+                   stream=None):
+    """fewbit_sketch_project: [rows (+ 1), features] in fp32 or bf16; with `column_sums` the extra last
+    row is scale * x.sum(0)."""
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.is_contiguous()
+    tokens, features = x.shape
+    total = rows + (1 if column_sums else 0)
+    out = torch.empty(total, features, dtype=out_dtype, device=x.device)
+    ws = sketch_workspace(x, total)
+    check(lib().fewbit_sketch_project(x.data_ptr(), out.data_ptr(), 1 if out_dtype == torch.bfloat16 else 0,
+                                      ws.data_ptr(), tokens, features, rows, int(column_sums),
+                                      SKETCH_KINDS.index(kind), scale, seed, offset, _stream(stream)),
+          'fewbit_sketch_project')
     return out
 
 

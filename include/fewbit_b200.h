@@ -156,12 +156,22 @@ FEWBIT_API int fewbit_piecewise_backward_host(int func, int dtype, const uint8_t
  *   workspace : fewbit_sketch_workspace_bytes(...) bytes of device memory (split-K partials;
  *               may be NULL when that is 0)
  *   kind      : 0 = N(0,1) entries ('gaussian'), 1 = +-1/2 entries ('rademacher')
+ * fewbit_sketch_project is the same product with the two passes that follow it in
+ * LinearGRPFunc.backward folded in (fewbit/functional/linear.py:199-217):
+ *   out_dtype   : FEWBIT_F32 or FEWBIT_BF16 -- the result is rounded once, in the kernel, instead of
+ *                 by a separate `.to(dtype)` pass over [P, D];
+ *   column_sums : non-zero appends one row of ones to S: out has rows + 1 rows and the last one is
+ *                 scale * sum_n X[n, :], i.e. `grad_output.sum(0)` (the bias gradient) for the price
+ *                 of one more sketch row.  Size the workspace for rows + 1.
  * fewbit_sketch_matrix writes S itself ([rows, cols] bf16) -- for tests and diagnostics only.
  */
 FEWBIT_API size_t fewbit_sketch_workspace_bytes(int64_t tokens, int features, int rows);
 FEWBIT_API int fewbit_sketch_forward(const void *x, float *out, void *workspace, int64_t tokens,
                                      int features, int rows, int kind, float scale, uint64_t seed,
                                      uint64_t offset, void *stream);
+FEWBIT_API int fewbit_sketch_project(const void *x, void *out, int out_dtype, void *workspace,
+                                     int64_t tokens, int features, int rows, int column_sums, int kind,
+                                     float scale, uint64_t seed, uint64_t offset, void *stream);
 FEWBIT_API int fewbit_sketch_matrix(void *s_bf16, int rows, int64_t cols, int kind, uint64_t seed,
                                     uint64_t offset, void *stream);
 

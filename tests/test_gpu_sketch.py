@@ -211,3 +211,46 @@ def test_transform_sketches_run_on_cuda(kind):
     y.backward(torch.randn_like(y))
     assert layer.weight.grad.shape == (32, 64) and layer.weight.grad.dtype == torch.float32
     assert torch.isfinite(layer.weight.grad).all() and x.grad is not None
+
+
+@pytest.mark.parametrize('kind', ['gaussian', 'rademacher'])
+@pytest.mark.parametrize('tokens,features,rows', [(16384, 768, 3276), (1000, 392, 161), (4096, 3072, 144), (130, 768, 7)])
+def test_projection_with_the_following_passes_folded_in(tokens, features, rows, kind):
+    """fewbit_sketch_project: the result rounded to bf16 in the kernel equals the fp32 result rounded by
+    torch, and with `column_sums` one more row of S is all ones, so the last output row is
+    scale * x.sum(0) -- LinearGRPFunc.backward's `.to(dtype)` and `grad_output.sum(0)` passes
+    (fewbit/functional/linear.py:199-217) without their trips through memory."""
+    torch.manual_seed(rows)
+    x = torch.randn(tokens, features, device=DEV).to(torch.bfloat16)
+    scale = 0.5
+    plain = native.sketch_forward(x, rows, 9, 8, kind, scale)
+    narrow = native.sketch_project(x, rows, 9, 8, kind, scale, torch.bfloat16)
+    assert narrow.dtype == torch.bfloat16 and torch.equal(narrow, plain.to(torch.bfloat16))
+    for dtype in (torch.float32, torch.bfloat16):
+        both = native.sketch_project(x, rows, 9, 8, kind, scale, dtype, column_sums=True)
+        assert both.shape == (rows + 1, features) and both.dtype == dtype
+        rms = plain.pow(2).mean().sqrt().item()
+        tol = 2e-3 * rms if dtype == torch.float32 else 2.0 ** -7 * plain.abs().max().item()
+        assert (both[:rows].float() - plain).abs().max().item() <= tol        # the sketch rows are unchanged
+        sums = x.float().sum(0) * scale
+        err = (both[rows].float() - sums).abs().max().item()
+        assert err <= (1e-3 if dtype == torch.float32 else 2.0 ** -7) * sums.abs().max().item() + 1e-4, err
+
+
+def test_bias_gradient_comes_out_of_the_projection_kernel():
+    """bf16 layer with a bias: the bias gradient is the extra row of the S G product (no separate
+    reduction over grad_output) and equals grad_output.sum(0) as torch rounds it."""
+    torch.manual_seed(11)
+    layer = fewbit.RandomizedLinear(256, 128, proj_dim=64, generator=torch.Generator(DEV).manual_seed(5)).to(DEV, torch.bfloat16)
+    x = torch.randn(8, 64, 256, device=DEV, dtype=torch.bfloat16, requires_grad=True)
+    g = torch.randn(8, 64, 128, device=DEV, dtype=torch.bfloat16)
+    layer(x).backward(g)
+    want = g.reshape(-1, 128).sum(0)
+    assert layer.bias.grad.dtype == torch.bfloat16
+    assert (layer.bias.grad.float() - want.float()).abs().max().item() <= 2.0 ** -7 * want.float().abs().max().item()
+    # fp32 layers keep torch's own fp32 sum (the kernel would round grad_output to bf16 first)
+    layer32 = fewbit.RandomizedLinear(256, 128, proj_dim=64, generator=torch.Generator(DEV).manual_seed(5)).to(DEV)
+    x32 = torch.randn(8, 64, 256, device=DEV, requires_grad=True)
+    g32 = torch.randn(8, 64, 128, device=DEV)
+    layer32(x32).backward(g32)
+    assert torch.equal(layer32.bias.grad, g32.reshape(-1, 128).sum(0))
