@@ -472,7 +472,9 @@ def side_measurements(dev, peak, traffic_table):
     flush = torch.ones(256 << 20, dtype=torch.float32, device=dev)     # 1 GiB: read before every timed launch
     sink = torch.zeros((), dtype=torch.float32, device=dev)
 
-    def timed(fn, reps=25, skip=5, group=3):
+    GROUP = 6
+
+    def timed(fn, reps=25, skip=5, group=GROUP):
         """Median over reps of (time of `group` launches, one per buffer set) / group.  Before every
         group the L2 is flushed by reading 1 GiB; the launches of a group touch different buffers,
         so every one of them finds its inputs in HBM.  The group is replayed from a CUDA graph:
@@ -499,15 +501,15 @@ def side_measurements(dev, peak, traffic_table):
                 ts.append(a.elapsed_time(b) / group)
         return statistics.median(ts)
 
-    where = ('128x128x3072 elements; median of 20 groups of 3 launches on 3 distinct buffer sets (replayed from a '
+    where = ('128x128x3072 elements; median of 20 groups of 6 launches on 6 distinct buffer sets (replayed from a '
              'CUDA graph), L2 flushed by reading 1 GiB before each group (inputs always come from HBM)')
     for tag, dtype, es in (('f32', torch.float32, 4), ('bf16', torch.bfloat16, 2)):
         borders, levels = store.get('gelu', 3, dev, dtype)
         bounds = borders[1:-1].contiguous()
-        xs = [(torch.randn(n, device=dev) * 2).to(dtype) for _ in range(3)]
-        gs = [torch.randn(n, device=dev).to(dtype) for _ in range(3)]
+        xs = [(torch.randn(n, device=dev) * 2).to(dtype) for _ in range(GROUP)]
+        gs = [torch.randn(n, device=dev).to(dtype) for _ in range(GROUP)]
         ys, gins = [torch.empty_like(t) for t in xs], [torch.empty_like(t) for t in gs]
-        states = [native.new_state(xs[0], 3) for _ in range(3)]
+        states = [native.new_state(xs[0], 3) for _ in range(GROUP)]
         nbytes = n * (2 * es) + n * 3 // 8
         for label, key, fn in (('fwd', f'gelu3_{tag}_forward',
                                 lambda k: native.stepwise_forward('gelu', xs[k], ys[k], states[k], 3, bounds)),
@@ -540,7 +542,7 @@ def side_measurements(dev, peak, traffic_table):
         out[f'sketch_{kind}_D768_TFLOPs'] = flops / (ms / 1e3) / 1e12
         rooflines.append(roofline_entry(
             f'sketch_{kind}_D768', flops, ms, tensor_peak, traffic_table.get('sketch_kernel'),
-            'N=16384 P=3276 D=768 bf16, median of 20 groups of 3 calls of fewbit_sketch_forward with preallocated output '
+            'N=16384 P=3276 D=768 bf16, median of 20 groups of 6 calls of fewbit_sketch_forward with preallocated output '
             'and workspace (projection kernel + split-K reduction), L2 flushed by reading 1 GiB before each group',
             bound='tensor', unit='TFLOP/s', scale=1e12, peak_source='MEASURED_PEAKS.json bf16_tflops (burst)'))
     out['sketch_peak_bf16_TFLOPs'] = tensor_peak
