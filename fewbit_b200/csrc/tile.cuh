@@ -48,8 +48,11 @@ constexpr int kSubtile = 256;  // elements per warp per round of 128-bit loads
 // the L2 prefetch wins (7-bit hardswish 85 % against 82 %).  profiles/r02_stream_modes.txt.
 #define FEWBIT_STREAM_MODE 2
 #endif
+#ifndef FEWBIT_STREAM_L2_MAXBITS
+#define FEWBIT_STREAM_L2_MAXBITS 8
+#endif
 template <typename T, int B> constexpr int stream_mode() {
-    return FEWBIT_STREAM_MODE != 2 ? FEWBIT_STREAM_MODE : (sizeof(T) == 2 && B >= 5 ? 1 : 0);
+    return FEWBIT_STREAM_MODE != 2 ? FEWBIT_STREAM_MODE : (sizeof(T) == 2 && B >= 5 && B <= FEWBIT_STREAM_L2_MAXBITS ? 1 : 0);
 }
 #ifndef FEWBIT_ST_MODE
 #define FEWBIT_ST_MODE 1  // 0: st.global   1: st.global.L1::no_allocate   2: st.global.cs
