@@ -48,6 +48,9 @@ constexpr int kSubtile = 256;  // elements per warp per round of 128-bit loads
 // the L2 prefetch wins (7-bit hardswish 85 % against 82 %).  profiles/r02_stream_modes.txt.
 #define FEWBIT_STREAM_MODE 2
 #endif
+#ifndef FEWBIT_L2_PIPELINE
+#define FEWBIT_L2_PIPELINE 1   // L2-prefetch mode: load the next half's registers before computing this one
+#endif
 #ifndef FEWBIT_STREAM_L2_MAXBITS
 #define FEWBIT_STREAM_L2_MAXBITS 8
 #endif
@@ -70,6 +73,23 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
     asm("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
 #else
     asm("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];"
+#endif
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// The same load as an ordered statement: it stays where it is written relative to the other volatile
+// statements (the shared-memory and global stores of the half computed meanwhile), which is what a
+// load issued one half AHEAD of its use needs -- left to itself the compiler sinks it to the use.
+__device__ __forceinline__ uint4 ldg_stream_ordered(const uint4 *p) {
+    uint4 r;
+#if FEWBIT_LD_MODE == 0
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+#elif FEWBIT_LD_MODE == 1
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+#else
+    asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];"
 #endif
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
@@ -130,6 +150,7 @@ template <> struct Subtile<float> {
         uint4 a, b;
     };
     static __device__ __forceinline__ Raw fetch(const uint4 *p) { return Raw{ldg_stream(p), ldg_stream(p + 32)}; }
+    static __device__ __forceinline__ Raw fetch_ordered(const uint4 *p) { return Raw{ldg_stream_ordered(p), ldg_stream_ordered(p + 32)}; }
     static __device__ __forceinline__ void widen(const Raw &r, float (&v)[8]) {
         v[0] = __uint_as_float(r.a.x), v[1] = __uint_as_float(r.a.y);
         v[2] = __uint_as_float(r.a.z), v[3] = __uint_as_float(r.a.w);
@@ -164,6 +185,7 @@ template <> struct Subtile<__nv_bfloat16> {
         uint4 a;
     };
     static __device__ __forceinline__ Raw fetch(const uint4 *p) { return Raw{ldg_stream(p)}; }
+    static __device__ __forceinline__ Raw fetch_ordered(const uint4 *p) { return Raw{ldg_stream_ordered(p)}; }
     static __device__ __forceinline__ void widen(const Raw &r, float (&v)[8]) {
         v[0] = bf16_lo(r.a.x), v[1] = bf16_hi(r.a.x), v[2] = bf16_lo(r.a.y), v[3] = bf16_hi(r.a.y);
         v[4] = bf16_lo(r.a.z), v[5] = bf16_hi(r.a.z), v[6] = bf16_lo(r.a.w), v[7] = bf16_hi(r.a.w);
@@ -625,6 +647,7 @@ template <class Op, typename T> struct ForwardStream {
         fetch_part = 0;
         fill = 0, fetch();
         fill = kSlot, fetch();
+        if constexpr (kMode == 1 && FEWBIT_L2_PIPELINE) fetch();     // registers run one half ahead: L2 requests three
         slot = 0;
     }
 
@@ -637,11 +660,25 @@ template <class Op, typename T> struct ForwardStream {
         const uint32_t put_at = pinned(S::put_address(strip, lane));
         const int64_t y_step = nwarps * (kParts * kHalf), out_step = nwarps * (kParts * kHalfChunks);
         ahead = pinned(ahead);
+        // L2-prefetch mode: the registers of the NEXT half are loaded (from L2: requested two halves ago)
+        // before this half is computed, so the L2 latency hides behind a half's worth of arithmetic.
+        typename Subtile<T>::Raw coming[H];
+        if constexpr (kMode == 1 && FEWBIT_L2_PIPELINE) {
+            coming[0] = Subtile<T>::fetch_ordered(now), coming[1] = Subtile<T>::fetch_ordered(now + Subtile<T>::kVectors);
+            now += kParts == 1 ? y_step : kHalf;
+        }
         for (int u = 0; u < mine; ++u, yl += y_step, out += out_step) {
 #pragma unroll
             for (int part = 0; part < kParts; ++part) {
                 typename Subtile<T>::Raw raw[H];
-                if constexpr (kMode == 1) {
+                if constexpr (kMode == 1 && FEWBIT_L2_PIPELINE) {
+                    raw[0] = coming[0], raw[1] = coming[1];
+                    if (part + 1 < kParts || u + 1 < mine) {
+                        coming[0] = Subtile<T>::fetch_ordered(now), coming[1] = Subtile<T>::fetch_ordered(now + Subtile<T>::kVectors);
+                        // after part 0 comes part 1 of the same unit; after the last part, the next unit
+                        now += (kParts == 1 || part == 0) ? (kParts == 1 ? y_step : y_step - (kParts - 1) * kHalf) : kHalf;
+                    }
+                } else if constexpr (kMode == 1) {
                     // the half was requested into L2 two halves ago: these loads are L2 hits
                     raw[0] = Subtile<T>::fetch(now), raw[1] = Subtile<T>::fetch(now + Subtile<T>::kVectors);
                     now += (kParts == 1 || part == 1) ? y_step - (kParts - 1) * kHalf : kHalf;
