@@ -1,6 +1,7 @@
 """Run-time knobs of the projection kernel, one process: python benchmarks/sketch_sweep.py "K=V,K=V" "K=V" ...
 Each argument is one configuration of FEWBIT_B200_SKETCH_* variables (without the prefix; "-" = defaults):
-UNITS (X ring entries), SLOTS (S ring entries), PREFETCH (stages of L2 prefetch), BN, SPLITK, PAIR, CLUSTER, DEBUG.
+SLOTS (S ring entries), BN, SPLITK, PAIR (0: no CTA pairs), CLUSTER (Cy without cta_group::2), DEBUG (1: no S
+generation, 4: no MMAs; timing only).  SWEEP_FEATURES / SWEEP_ROWS choose the shapes.
 Times fewbit_sketch_forward (N = 16384, P = 3276, D = 768 and 3072, both kinds) with output and workspace
 preallocated, 10 back-to-back calls, median of 5, and checks every result against a matmul with the materialised S."""
 import os
