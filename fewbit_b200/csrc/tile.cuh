@@ -51,6 +51,9 @@ constexpr int kSubtile = 256;  // elements per warp per round of 128-bit loads
 #ifndef FEWBIT_L2_PIPELINE
 #define FEWBIT_L2_PIPELINE 1   // L2-prefetch mode: load the next half's registers before computing this one
 #endif
+#ifndef FEWBIT_L2_AHEAD
+#define FEWBIT_L2_AHEAD 3      // halves between the L2 request and the computation (pipelined L2 mode)
+#endif
 #ifndef FEWBIT_STREAM_L2_MAXBITS
 #define FEWBIT_STREAM_L2_MAXBITS 8
 #endif
@@ -647,7 +650,8 @@ template <class Op, typename T> struct ForwardStream {
         fetch_part = 0;
         fill = 0, fetch();
         fill = kSlot, fetch();
-        if constexpr (kMode == 1 && FEWBIT_L2_PIPELINE) fetch();     // registers run one half ahead: L2 requests three
+        if constexpr (kMode == 1 && FEWBIT_L2_PIPELINE)              // registers run one half ahead: L2 requests three
+            for (int extra = 2; extra < FEWBIT_L2_AHEAD; ++extra) fetch();
         slot = 0;
     }
 
