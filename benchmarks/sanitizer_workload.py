@@ -36,10 +36,12 @@ for dtype in (torch.float32, torch.bfloat16):
         state = native.new_state(x, 1)
         native.piecewise_forward(name, x, y, state, p0, p1)
         native.piecewise_backward(name, state, x, gin, p0)
-# projection kernel: plain, 1 x 2 push cluster (rademacher, D = 768), CTA pair (gaussian, D = 768 and 1536)
-for tokens, features, rows, kind in ((1000, 72, 50, 'gaussian'), (4100, 768, 161, 'rademacher'),
-                                     (2048, 768, 333, 'gaussian'), (700, 1536, 40, 'gaussian')):
+# projection kernel: plain, 1 x 2 push cluster (two feature tiles that are not a pair, D = 512), CTA pair (D = 768 and
+# 1536, both kinds), and the variant that rounds to bf16 and appends the column sums
+for tokens, features, rows, kind in ((1000, 72, 50, 'gaussian'), (4100, 512, 161, 'rademacher'), (1300, 512, 70, 'gaussian'),
+                                     (2048, 768, 333, 'gaussian'), (700, 1536, 40, 'gaussian'), (4100, 768, 161, 'rademacher')):
     x = torch.randn(tokens, features, device=dev).to(torch.bfloat16)
     native.sketch_forward(x, rows, 7, 3, kind, 1.0 / rows)
+    native.sketch_project(x, rows, 7, 3, kind, 1.0 / rows, torch.bfloat16, column_sums=True)
 torch.cuda.synchronize()
 print('workload done')
