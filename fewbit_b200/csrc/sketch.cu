@@ -1107,6 +1107,14 @@ int fewbit_sketch_project(const void *x, void *out_any, int out_dtype, void *wor
     return (int)cudaGetLastError();
 }
 
+int fewbit_sketch_plan(int64_t tokens, int features, int rows, int kind, int sms, int out[8]) {
+    if (tokens < 0 || features <= 0 || rows <= 0 || (kind != 0 && kind != 1) || sms <= 0 || !out) return FEWBIT_EINVAL;
+    const Plan pl = plan(rows, features, tokens, kind, sms);
+    out[0] = pl.bn, out[1] = pl.split_k, out[2] = pl.cy, out[3] = pl.pair, out[4] = pl.kblocks_per_split;
+    out[5] = pl.s_slots, out[6] = pl.s_tile_bytes, out[7] = pl.smem_bytes;
+    return FEWBIT_OK;
+}
+
 int fewbit_sketch_matrix(void *s_bf16, int rows, int64_t cols, int kind, uint64_t seed, uint64_t offset,
                          void *stream) {
     if (!s_bf16 || rows <= 0 || cols <= 0 || (kind != 0 && kind != 1)) return FEWBIT_EINVAL;

@@ -44,6 +44,7 @@ PROTOTYPES = {
     'fewbit_sketch_forward': (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, C.c_float, C.c_uint64, C.c_uint64, _vp]),
     'fewbit_sketch_project': (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _i, _i, C.c_float, C.c_uint64, C.c_uint64, _vp]),
     'fewbit_sketch_matrix': (_i, [_vp, _i, _i64, _i, C.c_uint64, C.c_uint64, _vp]),
+    'fewbit_sketch_plan': (_i, [_i64, _i, _i, _i, _i, C.POINTER(C.c_int)]),
     'fewbit_launch_count': (_i64, []),
 }
 
@@ -224,6 +225,14 @@ def sketch_project(x, rows, seed, offset, kind='gaussian', scale=1.0, out_dtype=
                                       SKETCH_KINDS.index(kind), scale, seed, offset, _stream(stream)),
           'fewbit_sketch_project')
     return out
+
+
+def sketch_plan(tokens, features, rows, kind='gaussian', sms=148):
+    """The launch plan of the projection kernel for a shape (host only): dict of BN, split_k, sharing, rings."""
+    out = (C.c_int * 8)()
+    check(lib().fewbit_sketch_plan(tokens, features, rows, SKETCH_KINDS.index(kind), sms, out), 'fewbit_sketch_plan')
+    keys = ('bn', 'split_k', 'share', 'pair', 'stages_per_split', 's_slots', 's_tile_bytes', 'smem_bytes')
+    return dict(zip(keys, list(out)))
 
 
 def sketch_matrix(rows, cols, seed, offset, kind='gaussian', device='cuda', stream=None):

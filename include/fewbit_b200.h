@@ -174,6 +174,11 @@ FEWBIT_API int fewbit_sketch_project(const void *x, void *out, int out_dtype, vo
                                      float scale, uint64_t seed, uint64_t offset, void *stream);
 FEWBIT_API int fewbit_sketch_matrix(void *s_bf16, int rows, int64_t cols, int kind, uint64_t seed,
                                     uint64_t offset, void *stream);
+/* The launch plan fewbit_sketch_forward would use for a shape on a GPU with `sms` multiprocessors (no
+ * device needed; host tests check its invariants over many shapes).  plan[8] = { BN (sketch rows per CTA),
+ * split_k, CTAs sharing one generated S slot, 1 if those are a cta_group::2 pair, 64-token stages per
+ * split, S ring slots, bytes of one 64-token S tile, dynamic shared memory in bytes }. */
+FEWBIT_API int fewbit_sketch_plan(int64_t tokens, int features, int rows, int kind, int sms, int plan[8]);
 
 /* Number of kernels this library has launched in the calling process (for bench.py's
  * `gpu_launches`). */

@@ -138,3 +138,30 @@ def test_cpu_operators_reproduce_the_reference(golden_ops):
             out = torch.ops.fewbit.gelu(leaf, bounds, levels)
             out.backward(g)
             assert np.array_equal(leaf.grad.numpy().view(np.uint8), case['gin'].view(np.uint8)), case['key']
+
+
+@pytest.mark.parametrize('kind', ['gaussian', 'rademacher'])
+def test_projection_launch_plans_are_valid_for_every_shape(kind):
+    """fewbit_sketch_plan (host only): the invariants the projection kernel relies on, over a grid of
+    shapes -- MMA N a multiple of 16 within TMEM, S slots that span two stages (even stage count per
+    split, splits cover all tokens), 1024-byte aligned S tiles, rings inside 227 KB, pairs only on full
+    768-feature slabs."""
+    from fewbit_b200 import native
+    for sms in (148, 132):
+        for tokens in (1, 63, 64, 65, 1000, 4100, 16384, 100000):
+            for features in (8, 72, 384, 392, 512, 768, 1024, 1536, 3072, 4096):
+                for rows in (1, 15, 16, 144, 145, 160, 161, 3276, 3277, 10000):
+                    plan = native.sketch_plan(tokens, features, rows, kind, sms)
+                    where = f'{tokens}x{features}->{rows} {kind} sms={sms}: {plan}'
+                    bn, share = plan['bn'], plan['share']
+                    assert 64 <= bn <= 160 and bn % 16 == 0 and 3 * bn <= 512, where
+                    assert share in (1, 2) and (bn // 8) % share == 0, where
+                    assert not plan['pair'] or (share == 2 and features % 768 == 0), where
+                    stages = -(-max(tokens, 1) // 64)
+                    assert plan['split_k'] >= 1 and plan['stages_per_split'] % 2 == 0, where
+                    assert plan['split_k'] * plan['stages_per_split'] >= stages, where
+                    tile_rows = -(-(bn // 2 if plan['pair'] else bn) // 8) * 8
+                    assert plan['s_tile_bytes'] == tile_rows * 128 and plan['s_tile_bytes'] % 1024 == 0, where
+                    assert 2 <= plan['s_slots'] <= 4, where
+                    assert plan['smem_bytes'] == 3 * 49152 + plan['s_slots'] * 2 * plan['s_tile_bytes'] + 512 + 1024, where
+                    assert plan['smem_bytes'] <= 232448, where
