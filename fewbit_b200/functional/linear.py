@@ -277,7 +277,7 @@ class LinearGRPFunc(T.autograd.Function):
                     grad_proj = _native_sketch(grad_view, ctx.proj_features, *ctx.stream, ctx.matmul, 1.0,
                                                input_proj.dtype, with_bias)
                     if with_bias:
-                        grad_bias = grad_proj[ctx.proj_features]
+                        grad_bias = grad_proj[ctx.proj_features].clone()     # not a view: S G is freed after the GEMM
                         grad_proj = grad_proj[:ctx.proj_features]
                 else:  # feature count the TMA cannot address: same S, materialised
                     proj = T.ops.fewbit.sketch_matrix(grad_view, ctx.proj_features, grad_view.shape[0],
