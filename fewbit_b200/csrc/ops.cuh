@@ -37,6 +37,9 @@ struct NoScratch {
 // Tables shorter than 2^B - 1 are padded with +inf (never counted).
 // =====================================================================================
 
+#ifndef FEWBIT_ADAPTIVE_CELLS
+#define FEWBIT_ADAPTIVE_CELLS 1   // tables of 5+ bits: smallest power-of-two cell count that separates the borders
+#endif
 #ifndef FEWBIT_FEW_CELLS
 #define FEWBIT_FEW_CELLS 0   // A/B switch: try a bank-conflict-free 32-cell table first (bf16, 3-4 bits).  Measured:
                              // no effect (3-bit GELU bf16 86 % either way, profiles/r02_stream_modes.txt) -- with the
@@ -140,6 +143,23 @@ template <int kSize> __device__ __noinline__ uint32_t search_exact(uint32_t sort
     return k;
 }
 
+// The smallest cell count among `fewest`, 2 `fewest`, .. (below `most`) at which no two borders fall into one
+// cell, else `most`; leaves `map` set to it.  Borders are sorted, so cells are monotone and only neighbours can
+// clash.  One block-wide vote per candidate; nothing to vote on when fewest == most.
+template <typename T>
+__device__ __forceinline__ int choose_cells(CellMap &map, const T *bounds, int nbounds, int fewest, int most) {
+    int cells = fewest;
+    for (; cells < most; cells *= 2) {
+        map.set_cells(cells);
+        int clash = 0;
+        for (int i = threadIdx.x; i + 1 < nbounds; i += blockDim.x)
+            clash |= map.cell(to_float<T>(bounds[i])) == map.cell(to_float<T>(bounds[i + 1])) ? 1 : 0;
+        if (!__syncthreads_or(clash)) return cells;
+    }
+    map.set_cells(most);
+    return most;
+}
+
 // Borders -> cells, shared by both table layouts: fills s.bounds / s.bound_cell, then calls
 // `emit(cell, k, has_border)` for every cell with k = #{borders in earlier cells}; returns
 // (block-wide) whether some cell holds two or more borders.
@@ -225,7 +245,13 @@ template <typename T, int B> struct Bucketizer<T, B, false> {
     // bank conflicts (with 128 words ncu counted 2.6 wavefronts per gather, and the shared-memory
     // pipe is what bounds these kernels).  Most shipped 3-bit tables separate at 32 cells; if a
     // table does not, the full-size table is built instead.
-    static constexpr int kFewCells = (FEWBIT_FEW_CELLS && kOneGather && B <= 4) ? 32 : kCells;
+    // The table is built with the smallest cell count, from kMinCells up in powers of two, that keeps any two
+    // borders apart (choose_cells: one block-wide vote per candidate): 12 of the 13 shipped tables of 5-8 bits
+    // separate at half of kCells or less, and a table half the size is built in half the time and gathered with
+    // fewer bank conflicts (more lanes share a word) -- bf16 GELU 7 bits 79 -> 82 %, 8 bits 76 -> 80 % of the HBM
+    // peak (profiles/r02_adaptive_cells.txt).  kCells is the size that every shipped table separates at.
+    static constexpr int kMinCells = B >= 5 ? (FEWBIT_ADAPTIVE_CELLS ? 4 << B : kCells)
+                                            : (FEWBIT_FEW_CELLS && kOneGather && B >= 3) ? 32 : kCells;
     __device__ __forceinline__ void prepare(Scratch &s) {
         map.fit(bounds, nbounds);
         auto emit = [&](int c, int k, bool has) {
@@ -234,12 +260,8 @@ template <typename T, int B> struct Bucketizer<T, B, false> {
             else
                 s.lut[c] = (uint8_t)(k << kShift);
         };
-        map.set_cells(kFewCells);
-        crowded = build_cells<kSize>(map, kFewCells, bounds, nbounds, s, emit);
-        if (kFewCells != kCells && crowded) {
-            map.set_cells(kCells);
-            crowded = build_cells<kSize>(map, kCells, bounds, nbounds, s, emit);
-        }
+        const int cells = choose_cells(map, bounds, nbounds, kMinCells, kCells);
+        crowded = build_cells<kSize>(map, cells, bounds, nbounds, s, emit);
     }
     __device__ __forceinline__ uint32_t half(const Scratch &s, float x0, float x1, float x2, float x3) const {
         uint32_t c0, c1, c2, c3;

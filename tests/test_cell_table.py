@@ -78,14 +78,25 @@ def test_word_table_reproduces_the_bucket_search_for_every_bf16_value(bits):
         bounds = borders[1:-1].float().numpy()
         if len(np.unique(bounds)) != len(bounds):
             continue        # borders that collide after the cast to bf16: the kernel's exact path
-        # 3 and 4 bits: the kernel first tries 32 cells (one word per bank), then the full table
-        cell, words, crowded = build_words(bounds, bits, 32) if bits <= 4 else (None, None, True)
+        # the kernel builds the smallest table that separates the borders: 4 << bits cells, doubling up to the
+        # full size, from 5 bits on (choose_cells); at 3 and 4 bits 32 cells (one word per bank) is an A/B option
+        full = 2048 if bits == 6 else 16 << bits
+        cells = 32 if bits <= 4 else 4 << bits
+        cell, words, crowded = build_words(bounds, bits, cells)
         small += not crowded
-        if crowded:
-            cell, words, crowded = build_words(bounds, bits)
+        while crowded and cells < full:
+            cells = full if bits <= 4 else cells * 2
+            cell, words, crowded = build_words(bounds, bits, cells)
         if crowded:
             continue
         checked += 1
+        if cells < full:      # and the full-size table of the same borders gives the same codes
+            cell_full, words_full, crowded_full = build_words(bounds, bits, full)
+            assert not crowded_full, f'{name} {bits} bits: separates at {cells} cells but not at {full}'
+            wf = words_full[cell_full(x)]
+            with np.errstate(invalid='ignore'):
+                np.testing.assert_array_equal((wf & ((1 << bits) - 1)) + (wf.view(np.float32) < x),
+                                              (bounds[None, :] < x[:, None]).sum(axis=1))
         w = words[cell(x)]
         with np.errstate(invalid='ignore'):
             code = (w & ((1 << bits) - 1)) + (w.view(np.float32) < x)
@@ -96,6 +107,8 @@ def test_word_table_reproduces_the_bucket_search_for_every_bf16_value(bits):
         for j in range(copies):
             np.testing.assert_array_equal((w >> (bits * j)) & ((1 << bits) - 1), w & ((1 << bits) - 1))
     assert checked >= 8, f'only {checked} tables exercised the word layout at {bits} bits'
+    if bits >= 5:
+        assert small >= 5, f'only {small} of the {bits}-bit tables separate at the smallest cell count'
     if bits == 3:
         assert small >= 10, f'only {small} of the 3-bit tables fit the conflict-free 32-cell table'
 
