@@ -48,6 +48,10 @@ constexpr int kSubtile = 256;  // elements per warp per round of 128-bit loads
 // the L2 prefetch wins (7-bit hardswish 85 % against 82 %).  profiles/r02_stream_modes.txt.
 #define FEWBIT_STREAM_MODE 2
 #endif
+#ifndef FEWBIT_WHOLE_TILES_8
+#define FEWBIT_WHOLE_TILES_8 0   // bf16 8-bit streamed kernels: deal whole tiles (one flush per tile) instead of halves
+#endif
+template <typename T, int B> constexpr bool whole_tile_units() { return FEWBIT_WHOLE_TILES_8 && sizeof(T) == 2 && B == 8; }
 #ifndef FEWBIT_L2_PIPELINE
 #define FEWBIT_L2_PIPELINE 1   // L2-prefetch mode: load the next half's registers before computing this one
 #endif
@@ -596,7 +600,7 @@ template <class Op, typename T, int U> constexpr int ring_bytes() {
 // mopping up with unpipelined single subtiles cost ~10 % in the tail.
 template <class Op, typename T> struct ForwardStream {
     static constexpr int B = Op::kBits, H = 2;
-    static constexpr bool kWhole = Stager<T, B, 2 * H>::kTransposed;      // unit = tile (two halves)
+    static constexpr bool kWhole = Stager<T, B, 2 * H>::kTransposed || whole_tile_units<T, B>();      // unit = tile (two halves)
     static constexpr int kParts = kWhole ? 2 : 1;
     using S = Stager<T, B, kParts * H>;
     static constexpr int kHalf = H * Subtile<T>::kVectors;                // 128-bit vectors per half
@@ -712,7 +716,7 @@ __global__ void __launch_bounds__(kThreads, MINB) forward_tiles_kernel(const T *
                                                                 int64_t ntiles, Op op) {
     constexpr int B = Op::kBits;
     constexpr bool kRing = streams_input<Op, T, U>();
-    constexpr int kStaged = kRing && !Stager<T, B, U>::kTransposed ? U / 2 : U;   // subtiles staged at a time
+    constexpr int kStaged = kRing && !Stager<T, B, U>::kTransposed && !whole_tile_units<T, B>() ? U / 2 : U;   // subtiles staged at a time
     constexpr int kStrip = Stager<T, B, kStaged>::kBytes > Stager<T, B, 1>::kBytes ? Stager<T, B, kStaged>::kBytes
                                                                                     : Stager<T, B, 1>::kBytes;
     __shared__ alignas(16) uint8_t strips[kWarps][(kStrip + 15) / 16 * 16];
