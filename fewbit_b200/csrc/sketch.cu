@@ -6,7 +6,8 @@
 //         with counter (n / 8, p, offset) gives eight normals (Box-Muller on 16-bit uniforms),
 //         one call with counter (n / 128, p, offset) gives 128 signs -- so forward and backward
 //         regenerate the same S.
-//   out : [P, D] fp32
+//   out : [P, D] fp32 (fewbit_sketch_forward) or fp32 / bf16 with an optional extra row of column sums
+//         (fewbit_sketch_project: one row of S is all ones -- the bias gradient of the backward pass)
 // Replaces `proj = randn(P, N); proj_input = (proj @ input_view) / P` and `proj @ grad_output`
 // of the reference (fewbit/functional/linear.py:133-137, 196-199), which writes S (214 MB at
 // RoBERTa shapes) to HBM twice per layer and multiplies in fp32 on the CUDA cores.
@@ -60,7 +61,8 @@
 //    hand-over).
 // Tried and dropped (profiles/r01_sketch_kernel.md, r02_sketch_unit_ring.txt): sharing X between row
 // tiles by TMA multicast, clusters of 8 along y, an X ring in 16 KB units with one commit each, L2
-// prefetch ahead of the TMA, the leader loading the peer's X boxes, more generator warps.
+// prefetch ahead of the TMA, the leader loading the peer's X boxes, more generator warps, split-K summed inside a
+// 2 x 1 x 3 cluster through distributed shared memory (profiles/r02_sketch_trace.md).
 // A stage or slot may be overwritten only when every CTA of the cluster has consumed it:
 // tcgen05.commit multicasts its arrival to the `empty` barriers of all CTAs of the cluster.
 // FEWBIT_B200_SKETCH_TRACE=1 prints one CTA's timeline per call (benchmarks/sketch_trace.py).
