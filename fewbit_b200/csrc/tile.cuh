@@ -48,6 +48,9 @@ constexpr int kSubtile = 256;  // elements per warp per round of 128-bit loads
 // the L2 prefetch wins (7-bit hardswish 85 % against 82 %).  profiles/r02_stream_modes.txt.
 #define FEWBIT_STREAM_MODE 2
 #endif
+#ifndef FEWBIT_ORDERED_PIPE
+#define FEWBIT_ORDERED_PIPE 0    // forward kernels that do not stream: software pipeline of ordered register loads
+#endif
 #ifndef FEWBIT_WHOLE_TILES_8
 #define FEWBIT_WHOLE_TILES_8 0   // bf16 8-bit streamed kernels: deal whole tiles (one flush per tile) instead of halves
 #endif
@@ -539,18 +542,20 @@ __device__ __forceinline__ void forward_loop(const Op &op, const typename Op::Sc
         uint4 *out = pinned(reinterpret_cast<uint4 *>(state) + me * kChunks + lane);
         const uint32_t put_at = pinned(Stager<T, B, U>::put_address(strip, lane));
         const int64_t step = nwarps * kVectors, out_step = nwarps * kChunks;
-        if constexpr (Op::kHeavy && U % 2 == 0 && FEWBIT_PREFETCH == 1) {
+        if constexpr (Op::kHeavy && U % 2 == 0 && (FEWBIT_PREFETCH == 1 || FEWBIT_ORDERED_PIPE)) {
             constexpr int H = U / 2, kHalf = H * Subtile<T>::kVectors;
             typename Subtile<T>::Raw first[H], second[H];
 #pragma unroll
-            for (int h = 0; h < H; ++h) first[h] = Subtile<T>::fetch(xl + h * Subtile<T>::kVectors);
+            // ordered loads: each half's registers are requested while the half before it is computed
+            // (left unordered, the compiler sinks them to their first use)
+            for (int h = 0; h < H; ++h) first[h] = Subtile<T>::fetch_ordered(xl + h * Subtile<T>::kVectors);
             for (int64_t r = 0; r < rounds; ++r, yl += step, out += out_step) {
 #pragma unroll
-                for (int h = 0; h < H; ++h) second[h] = Subtile<T>::fetch(xl + kHalf + h * Subtile<T>::kVectors);
+                for (int h = 0; h < H; ++h) second[h] = Subtile<T>::fetch_ordered(xl + kHalf + h * Subtile<T>::kVectors);
                 forward_half<Op, T, Stager<T, B, U>, kExact, 0, 0, H>(op, scratch, first, yl, put_at, lane);
                 if (r + 1 < rounds) xl += step;     // the last round fetches its own first half again
 #pragma unroll
-                for (int h = 0; h < H; ++h) first[h] = Subtile<T>::fetch(xl + h * Subtile<T>::kVectors);
+                for (int h = 0; h < H; ++h) first[h] = Subtile<T>::fetch_ordered(xl + h * Subtile<T>::kVectors);
                 forward_half<Op, T, Stager<T, B, U>, kExact, H, H, H>(op, scratch, second, yl, put_at, lane);
                 Stager<T, B, U>::flush(strip, out, lane);
             }
