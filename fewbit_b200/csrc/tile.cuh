@@ -48,6 +48,9 @@ constexpr int kSubtile = 256;  // elements per warp per round of 128-bit loads
 // the L2 prefetch wins (7-bit hardswish 85 % against 82 %).  profiles/r02_stream_modes.txt.
 #define FEWBIT_STREAM_MODE 2
 #endif
+#ifndef FEWBIT_BACKWARD_PIPE
+#define FEWBIT_BACKWARD_PIPE 0   // backward kernels: request the next tile (ordered loads) before computing this one
+#endif
 #ifndef FEWBIT_ORDERED_PIPE
 #define FEWBIT_ORDERED_PIPE 0    // forward kernels that do not stream: software pipeline of ordered register loads
 #endif
@@ -759,8 +762,52 @@ __global__ void __launch_bounds__(kThreads, MINB) backward_tiles_kernel(const ui
     const int64_t nwarps = (int64_t)gridDim.x * kWarps;
     const int64_t me = (int64_t)blockIdx.x * kWarps + warp;
     const int64_t even = ntiles / nwarps * nwarps;
-    for (int64_t tile = me; tile < even; tile += nwarps)
-        backward_chunk<Op, T, U>(op, state, gout, gin, strip, tile * U, lane);
+    if constexpr (FEWBIT_BACKWARD_PIPE) {
+        // The next tile's gradients and packed codes are requested (ordered loads) before this tile is decoded and
+        // multiplied: one tile's worth of loads is in flight during every compute phase.
+        constexpr int kBytes = U * subtile_bytes<B>(), kChunks = kBytes / 16, kMine = (kChunks + 31) / 32;
+        typename Subtile<T>::Raw g_next[U];
+        uint4 s_next[kMine];
+        auto request = [&](int64_t tile) {
+            const uint4 *gp = reinterpret_cast<const uint4 *>(gout + tile * U * kSubtile) + lane;
+#pragma unroll
+            for (int u = 0; u < U; ++u) g_next[u] = Subtile<T>::fetch_ordered(gp + u * Subtile<T>::kVectors);
+            const uint4 *packed = reinterpret_cast<const uint4 *>(state + tile * (int64_t)kBytes);
+#pragma unroll
+            for (int k = 0; k < kMine; ++k)
+                if (lane + 32 * k < kChunks) s_next[k] = ldg_stream_ordered(packed + lane + 32 * k);
+        };
+        if (me < even) request(me);
+        for (int64_t tile = me; tile < even; tile += nwarps) {
+            typename Subtile<T>::Raw g_now[U];
+            uint4 s_now[kMine];
+#pragma unroll
+            for (int u = 0; u < U; ++u) g_now[u] = g_next[u];
+#pragma unroll
+            for (int k = 0; k < kMine; ++k) s_now[k] = s_next[k];
+            if (tile + nwarps < even) request(tile + nwarps);
+            uint4 *dst = reinterpret_cast<uint4 *>(strip);
+#pragma unroll
+            for (int k = 0; k < kMine; ++k)
+                if (lane + 32 * k < kChunks) dst[lane + 32 * k] = s_now[k];
+            __syncwarp();
+            T *dt = gin + tile * U * kSubtile;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float v[8];
+                uint32_t code[8];
+                Subtile<T>::widen(g_now[u], v);
+                fetch_codes<T, B>(reinterpret_cast<const uint32_t *>(strip + u * subtile_bytes<B>()), lane, code);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = op.factor(code[j]) * v[j];
+                Subtile<T>::store(dt + u * kSubtile, lane, v);
+            }
+            __syncwarp();
+        }
+    } else {
+        for (int64_t tile = me; tile < even; tile += nwarps)
+            backward_chunk<Op, T, U>(op, state, gout, gin, strip, tile * U, lane);
+    }
     for (int64_t sub = even * U + me; sub < ntiles * U; sub += nwarps)
         backward_chunk<Op, T, 1>(op, state, gout, gin, strip, sub, lane);
 }
